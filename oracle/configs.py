@@ -1,0 +1,166 @@
+"""The five BASELINE.json configs, written against the oracle exactly as the
+reference's examples write them against surjectors.  TEST INFRASTRUCTURE.
+
+cfg1  README.md:30-45                       Chain([Slice(5, dec), LULinear(5)]), dim 10
+cfg2  examples/coupling_inference_surjection.py:40-67     20 -> 10 -> 10 -> 5
+cfg3  examples/autoregressive_inference_surjection.py:35-67
+cfg4  docs/notebooks/dimension_reduction.ipynb:600-640 scaled
+cfg5  examples/conditional_density_estimation.py:28-76 scaled
+
+Each `make_cfgN(**scale)` returns `flow(y=..., x=...) -> lp` to be wrapped in
+`hk.transform`.  Scale arguments default to BASELINE sizes; tests pass smaller ones.
+"""
+
+import numpy as np
+import torch
+
+from oracle import hk
+from oracle import surjectors as S
+
+
+def _dec(n_dim, hidden):
+  return S.normal_decoder(n_dim, hidden)
+
+
+def make_cfg1(dim=10, n_keep=5, dec_hidden=(32, 32)):
+  def flow(y, x=None):
+    transform = S.Chain([S.Slice(n_keep, _dec(dim - n_keep, dec_hidden)), S.LULinear(n_keep)])
+    td = S.TransformedDistribution(S.standard_normal_base(n_keep, y.dtype), transform)
+    return td.log_prob(y, x)
+
+  return flow
+
+
+def make_cfg2(dim=20, cond_hidden=(8, 8), dec_hidden=(4, 4)):
+  def bijector_fn(params):
+    shift, log_scale = S.split(params, 2, -1)
+    return S.ScalarAffine(shift, torch.exp(log_scale))
+
+  def flow(y, x=None):
+    n_dim = dim
+    layers = []
+    for i in range(3):
+      if i != 1:
+        layer = S.AffineMaskedCouplingInferenceFunnel(
+          n_keep=int(n_dim / 2),
+          decoder=_dec(int(n_dim / 2), dec_hidden),
+          conditioner=S.make_mlp(tuple(cond_hidden) + (n_dim * 2,)),
+        )
+        n_dim = int(n_dim / 2)
+      else:
+        layer = S.MaskedCoupling(
+          mask=S.make_alternating_binary_mask(n_dim, i % 2 == 0),
+          bijector_fn=bijector_fn,
+          conditioner=S.make_mlp(list(cond_hidden) + [n_dim * 2]),
+        )
+      layers.append(layer)
+    td = S.TransformedDistribution(S.standard_normal_base(n_dim, y.dtype), S.Chain(layers))
+    return td.log_prob(y, x)
+
+  return flow
+
+
+def make_cfg3(dim=20, made_hidden=(8, 8), dec_hidden=(4, 4)):
+  def made_bijector_fn(params):
+    means, log_scales = S.unstack(params, -1)
+    return S.Inverse(S.ScalarAffine(means, torch.exp(log_scales)))
+
+  def flow(y, x=None):
+    n_dim = dim
+    layers = []
+    for i in range(3):
+      if i != 1:
+        layer = S.AffineMaskedAutoregressiveInferenceFunnel(
+          n_keep=int(n_dim / 2),
+          decoder=_dec(int(n_dim / 2), dec_hidden),
+          conditioner=S.MADE(int(n_dim / 2), list(made_hidden), 2),
+        )
+        n_dim = int(n_dim / 2)
+      else:
+        layer = S.MaskedAutoregressive(conditioner=S.MADE(n_dim, list(made_hidden), 2), bijector_fn=made_bijector_fn)
+      layers.append(layer)
+    td = S.TransformedDistribution(S.standard_normal_base(n_dim, y.dtype), S.Chain(layers))
+    return td.log_prob(y, x)
+
+  return flow
+
+
+def make_cfg4(dim=64, n_keep=16, hidden=(256, 256), n_bins=64, n_pre=4, n_post=4, rng=(-3.0, 3.0)):
+  n_par = 3 * n_bins + 1
+
+  def cond(d):
+    return hk.Sequential([S.make_mlp(tuple(hidden) + (d * n_par,)), hk.Reshape((d, n_par))])
+
+  def flow(y, x=None):
+    layers = []
+    for i in range(n_pre):
+      layers.append(
+        S.RationalQuadraticSplineMaskedCoupling(
+          S.make_alternating_binary_mask(dim, i % 2 == 0), cond(dim), rng[0], rng[1]
+        )
+      )
+    layers.append(
+      S.RationalQuadraticSplineMaskedCouplingInferenceFunnel(
+        n_keep, _dec(dim - n_keep, hidden), cond(dim), rng[0], rng[1]
+      )
+    )
+    for i in range(n_post):
+      layers.append(
+        S.RationalQuadraticSplineMaskedCoupling(
+          S.make_alternating_binary_mask(n_keep, i % 2 == 0), cond(n_keep), rng[0], rng[1]
+        )
+      )
+    td = S.TransformedDistribution(S.standard_normal_base(n_keep, y.dtype), S.Chain(layers))
+    return td.log_prob(y, x)
+
+  return flow
+
+
+def make_cfg5(dim=128, hidden=(512, 512), n_layers=16):
+  def bijector_fn(params):
+    means, log_scales = S.unstack(params, -1)
+    return S.ScalarAffine(means, torch.exp(log_scales))
+
+  def flow(y, x=None):
+    layers = []
+    order = np.arange(dim)
+    for _ in range(n_layers):
+      layers.append(
+        S.MaskedAutoregressive(
+          bijector_fn=bijector_fn,
+          conditioner=S.MADE(
+            dim, list(hidden), 2, w_init=hk.initializers.TruncatedNormal(0.01), b_init=hk.zeros
+          ),
+        )
+      )
+      layers.append(S.LULinear(dim))
+      order = order[::-1]
+      layers.append(S.Permutation(order, 1))
+    layers = layers[:-1]
+    td = S.TransformedDistribution(S.standard_normal_base(dim, y.dtype), S.Chain(layers))
+    return td.log_prob(y, x)
+
+  return flow
+
+
+def randomize(params, seed, w_std=0.3, b_val=None, b_std=0.1):
+  """Replace haiku-default inits by non-trivial values so every transform is exercised
+  (mirrors masked_coupling_test.py:78-82: TruncatedNormal(1.0) weights, ones bias)."""
+  rng = np.random.Generator(np.random.PCG64(seed))
+  out = {}
+  for mod, bucket in params.items():
+    out[mod] = {}
+    for name, val in bucket.items():
+      if name == "w":
+        fan_in = val.shape[0]
+        new = rng.standard_normal(val.shape) * (w_std / np.sqrt(max(fan_in, 1)) * np.sqrt(8.0))
+      elif name == "b":
+        new = rng.standard_normal(val.shape) * b_std if b_val is None else np.full(val.shape, b_val)
+      elif name in ("lower_entries", "upper_entries"):
+        new = rng.standard_normal(val.shape) * (0.3 / np.sqrt(max(val.shape[0], 1)) ** 0.5)
+      elif name == "diag_entries":
+        new = 1.0 + 0.3 * rng.standard_normal(val.shape)
+      else:
+        new = val.numpy()
+      out[mod][name] = torch.as_tensor(np.asarray(new), dtype=val.dtype).reshape(val.shape).clone()
+  return out
