@@ -1,0 +1,180 @@
+/* surj_b200.h -- C ABI of the B200 (sm_100a) implementation of surjectors' batched
+ * flow log-likelihood and its gradient.
+ *
+ * This is the drop-in boundary for ONE path of dirmeier/surjectors v0.3.4 (all file:line
+ * citations are relative to the reference checkout): `TransformedDistribution.log_prob`
+ * through a `Chain` and its VJP.  In the reference the callee below this boundary is
+ * XLA; the binding a maintainer would add is a `jax.ffi.ffi_call` per entry point
+ * wrapped in `jax.custom_vjp`.  Everything is plain pointers and
+ * sizes; there are no torch / JAX types in any signature.
+ *
+ * Conventions
+ *   - all device arrays are float32, row-major, batch-leading: y[B, D], x[B, Dx], lp[B];
+ *   - device pointers must be 16-byte aligned;
+ *   - `params` is ONE flat float32 device buffer; every layer descriptor carries the float
+ *     offsets of its haiku parameters inside it (w:[in,out] row-major, b:[out]);
+ *   - every call only ENQUEUES work on `stream` (no host sync, no allocation on the hot path:
+ *     scratch comes from the caller-provided workspace) and is CUDA-graph capturable;
+ *   - functions return 0 on success, a negative SURJ_E_* code otherwise;
+ *     `surj_last_error()` returns a thread-local message.
+ */
+#ifndef SURJ_B200_H_
+#define SURJ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURJ_ABI_VERSION 1
+#define SURJ_MAX_NET_LAYERS 8
+
+enum SurjStatus {
+  SURJ_OK = 0,
+  SURJ_E_INVALID = -1,     /* bad descriptor / argument (reference: ValueError at construction) */
+  SURJ_E_UNSUPPORTED = -2, /* structure the kernels do not implement (reference: NotImplementedError) */
+  SURJ_E_CUDA = -3,        /* CUDA runtime error; message holds cudaGetErrorString */
+  SURJ_E_WORKSPACE = -4    /* workspace too small / misaligned */
+};
+
+/* Layer kinds == the reference classes on the hot path. */
+enum SurjLayerKind {
+  SURJ_LAYER_COUPLING = 0,        /* MaskedCoupling                 _src/bijectors/masked_coupling.py:73-85 */
+  SURJ_LAYER_COUPLING_FUNNEL = 1, /* MaskedCouplingInferenceFunnel  _src/surjectors/masked_coupling_inference_funnel.py:72-91 */
+  SURJ_LAYER_MAF = 2,             /* MaskedAutoregressive           _src/bijectors/masked_autoregressive.py:73-79 */
+  SURJ_LAYER_MAF_FUNNEL = 3,      /* MaskedAutoregressiveInferenceFunnel _src/surjectors/masked_autoregressive_inference_funnel.py:77-90 */
+  SURJ_LAYER_SLICE = 4,           /* Slice                          _src/surjectors/slice.py:58-68 */
+  SURJ_LAYER_LU = 5,              /* LULinear                       _src/bijectors/lu_linear.py:68-90 */
+  SURJ_LAYER_PERMUTATION = 6      /* Permutation                    _src/bijectors/permutation.py:30-37 */
+};
+
+/* Inner bijector returned by the user's bijector_fn (distrax semantics). */
+enum SurjInner {
+  SURJ_INNER_AFFINE = 0,     /* ScalarAffine(m, exp(s)):           z = (y - m) e^{-s}, ld = -s */
+  SURJ_INNER_AFFINE_INV = 1, /* Inverse(ScalarAffine(m, exp(s))):  z = e^{s} y + m,    ld = +s */
+  SURJ_INNER_RQS = 2,        /* RationalQuadraticSpline(theta, lo, hi): spline inverse */
+  SURJ_INNER_RQS_INV = 3     /* Inverse(RationalQuadraticSpline):  spline forward */
+};
+
+/* How bijector_fn slices the conditioner output for affine bijectors (quirk Q5). */
+enum SurjLayout {
+  SURJ_LAYOUT_SPLIT = 0,      /* jnp.split(theta, 2, -1): shift = theta[:D], log_scale = theta[D:] */
+  SURJ_LAYOUT_INTERLEAVED = 1 /* unstack(theta[.., D, 2], -1): shift = theta[2d], log_scale = theta[2d+1] */
+};
+
+enum SurjActivation {
+  SURJ_ACT_IDENTITY = 0, SURJ_ACT_RELU = 1, SURJ_ACT_SWISH = 2, SURJ_ACT_TANH = 3, SURJ_ACT_SIGMOID = 4,
+  SURJ_ACT_SOFTPLUS = 5, SURJ_ACT_GELU = 6, SURJ_ACT_ELU = 7, SURJ_ACT_LEAKY_RELU = 8
+};
+
+/* hk.nets.MLP / make_mlp (_src/conditioners/mlp.py:7-29), possibly followed by hk.Linear
+ * layers inside an hk.Sequential: a stack of n_layers Linear layers. */
+typedef struct SurjMlpDesc {
+  int32_t n_layers;                         /* 0 = absent */
+  int32_t widths[SURJ_MAX_NET_LAYERS + 1];  /* widths[0] = input width; widths[l+1] = output of layer l */
+  int32_t act[SURJ_MAX_NET_LAYERS];         /* activation applied after layer l */
+  int64_t w_off[SURJ_MAX_NET_LAYERS];       /* float offset of w[widths[l], widths[l+1]] */
+  int64_t b_off[SURJ_MAX_NET_LAYERS];       /* float offset of b[widths[l+1]]; -1 = no bias */
+} SurjMlpDesc;
+
+/* MADE (_src/conditioners/nn/made.py:26-91).  Masks are rebuilt from (input_size, hidden,
+ * n_params) with TFP's _make_dense_autoregressive_masks algorithm (made.py:54-56). */
+typedef struct SurjMadeDesc {
+  int32_t input_size;                       /* 0 = absent */
+  int32_t n_params;
+  int32_t n_hidden;
+  int32_t hidden[SURJ_MAX_NET_LAYERS];
+  int32_t act;                              /* between masked layers, not after the last */
+  int32_t ctx_dim;                          /* width of the conditioning input of the context Linear; 0 = none */
+  int64_t w_off[SURJ_MAX_NET_LAYERS + 1];   /* n_hidden + 1 masked layers */
+  int64_t b_off[SURJ_MAX_NET_LAYERS + 1];
+  int64_t ctx_w_off, ctx_b_off;             /* hk.Linear(hidden[0]) on the context (made.py:80-84) */
+} SurjMadeDesc;
+
+typedef struct SurjLayerDesc {
+  int32_t kind;        /* SurjLayerKind */
+  int32_t dim_in;      /* event width entering the layer */
+  int32_t dim_out;     /* event width leaving it (n_keep for Slice / funnels) */
+  int32_t use_x;       /* 1 if the layer consumes the chain's conditioning input x */
+  int32_t inner;       /* SurjInner */
+  int32_t layout;      /* SurjLayout (affine inners on couplings; MADE output is always interleaved) */
+  int32_t n_bins;      /* RQS: K, conditioner emits 3K+1 values per dim */
+  float range_min, range_max;
+  const uint8_t* mask;         /* COUPLING: [dim_in], 1 = passes through & feeds the conditioner */
+  const int32_t* permutation;  /* PERMUTATION: [dim_in] (the forward permutation, as the reference stores it) */
+  SurjMlpDesc conditioner;     /* COUPLING / COUPLING_FUNNEL */
+  SurjMadeDesc made;           /* MAF / MAF_FUNNEL */
+  SurjMlpDesc decoder;         /* SLICE / funnels: MLP -> split -> Independent(Normal(mu, exp(log_sigma))) */
+  int64_t lu_lower_off, lu_upper_off, lu_diag_off; /* LU: haiku params lower_entries, upper_entries, diag_entries */
+} SurjLayerDesc;
+
+typedef struct SurjPlan SurjPlan;
+typedef void* SurjStream; /* cudaStream_t */
+
+enum SurjPlanMode {
+  SURJ_MODE_AUTO = 0,  /* fused whole-chain kernel when one is compiled in for this chain, else per-layer */
+  SURJ_MODE_FUSED = 1, /* require the fused whole-chain kernel (error if not compiled in) */
+  SURJ_MODE_LAYERED = 2 /* generic per-layer kernels (any width) */
+};
+
+/* What is added to the summed likelihood contributions of the layers. */
+enum SurjBase {
+  SURJ_BASE_STANDARD_NORMAL = 0, /* lp = Independent(Normal(0, 1)).log_prob(z) + lc   (TransformedDistribution.log_prob) */
+  SURJ_BASE_NONE = 1             /* lp = lc   (Surjector.inverse_and_likelihood_contribution on its own) */
+};
+
+/* --- plan: replaces tracing the chain under jax.jit (examples/coupling_inference_surjection.py:81) */
+int surj_plan_create(const SurjLayerDesc* layers, int32_t n_layers, int32_t dim_in, int32_t dim_x, int64_t n_params,
+                     int32_t mode, int32_t base, SurjPlan** out);
+void surj_plan_destroy(SurjPlan* plan);
+/* canonical 64-bit key of the chain structure (what fused kernels are registered under) */
+uint64_t surj_plan_key(const SurjPlan* plan);
+int surj_chain_key(const SurjLayerDesc* layers, int32_t n_layers, int32_t dim_in, int32_t dim_x, int64_t n_params,
+                   uint64_t* key_out);
+int32_t surj_plan_is_fused(const SurjPlan* plan);
+int32_t surj_plan_dim_out(const SurjPlan* plan);
+/* number of kernels one fwd / one bwd call launches (for launch accounting) */
+int32_t surj_plan_launches(const SurjPlan* plan, int32_t backward);
+
+/* bytes of device scratch a call with batch B needs (backward != 0 for the VJP) */
+size_t surj_plan_workspace_bytes(const SurjPlan* plan, int64_t batch, int32_t backward);
+
+/* --- TransformedDistribution.inverse_and_log_prob (_src/distributions/transformed_distribution.py:72-93)
+ * with base = Independent(Normal(0, 1)).  z_out may be NULL.  x may be NULL iff dim_x == 0. */
+int surj_chain_logprob_fwd(const SurjPlan* plan, SurjStream stream, const float* y, const float* x, const float* params,
+                           float* z_out, float* lp_out, void* workspace, size_t workspace_bytes, int64_t batch);
+
+/* --- VJP of (z, lp) w.r.t. params (and optionally y, x): what jax.value_and_grad differentiates at
+ * examples/coupling_inference_surjection.py:83-87.  Cotangent of lp is g_lp[B], or the constant
+ * g_scale when g_lp == NULL (g_scale = -1 gives loss = -sum(lp)); g_z[B, dim_out] is the optional
+ * cotangent of the latent z (NULL = zero).  Outputs:
+ *   g_params[n_params]  (overwritten),  loss_out[1] = g_scale * sum(lp) when g_lp == NULL (may be NULL),
+ *   lp_out[B], g_y[B, D], g_x[B, Dx]  optional (NULL to skip). */
+int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, const float* y, const float* x, const float* params,
+                           const float* g_lp, float g_scale, const float* g_z, float* g_params, float* loss_out,
+                           float* lp_out,
+                           float* g_y, float* g_x, void* workspace, size_t workspace_bytes, int64_t batch);
+
+/* --- optax.adam(lr) update (optax 0.2.4: b1, b2, eps, bias-corrected, eps_root = 0), fused over the
+ * flat buffers; `count` is a device int32 that is incremented by the kernel. */
+int surj_adam_step(SurjStream stream, float* params, const float* grads, float* mu, float* nu, int32_t* count,
+                   int64_t n, float lr, float b1, float b2, float eps, float grad_scale);
+
+/* --- helpers */
+/* TFP _make_dense_autoregressive_masks restated; writes n_hidden+1 masks ([in, out] row-major,
+ * bytes 0/1) back to back into out (size queried by passing out == NULL). */
+int64_t surj_made_masks(int32_t n_params, int32_t input_size, const int32_t* hidden, int32_t n_hidden, uint8_t* out);
+/* Permutation inverse index exactly as permutation.py:31-36 computes it (int32). */
+int surj_permutation_inverse(const int32_t* permutation, int32_t n, int32_t* inverse_out);
+
+const char* surj_last_error(void);
+int32_t surj_abi_version(void);
+/* number of fused whole-chain kernels compiled into this library */
+int32_t surj_registry_size(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURJ_B200_H_ */

@@ -1,0 +1,393 @@
+"""Host-side mirror of the reference's Surjector / Bijector classes on the log_prob path.
+
+Same class names, constructor signatures and error behaviour as dirmeier/surjectors v0.3.4
+(citations relative to /root/reference/).  Where the reference's methods trace JAX ops, these
+record a `LayerSpec` (surjectors_b200/_spec.py); the arithmetic happens in the sm_100a kernels
+behind include/surj_b200.h.  User-supplied `conditioner`, `bijector_fn` and `decoder` callables
+are invoked on symbols and pattern-matched; anything the kernels do not implement raises
+`NotImplementedError` -- there is no eager / CPU fallback.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from surjectors_b200 import _abi, _sym, hk
+from surjectors_b200._spec import ChainSpec, LayerSpec, MadeSpec, MlpSpec
+
+
+def _mlp_spec(net: _sym.NetSym) -> MlpSpec:
+  widths = [net.source.width] + [l.n_out for l in net.layers]
+  return MlpSpec(widths=widths, acts=[l.act for l in net.layers], w=[l.w for l in net.layers],
+                 b=[l.b for l in net.layers])
+
+
+def _is_array(v):
+  return isinstance(v, torch.Tensor)
+
+
+# ------------------------------------------------------------------ protocol
+class Surjector:
+  """surjectors/_src/surjectors/surjector.py:9-99."""
+
+  def __call__(self, method, **kwargs):
+    return getattr(self, method)(**kwargs)
+
+  def inverse_and_likelihood_contribution(self, y, x=None, **kwargs):
+    return self._inverse_and_likelihood_contribution(y, x=x, **kwargs)
+
+  def forward_and_likelihood_contribution(self, z, x=None, **kwargs):
+    return self._forward_and_likelihood_contribution(z, x=x, **kwargs)
+
+  def forward(self, z, x=None, **kwargs):
+    return self.forward_and_likelihood_contribution(z, x=x, **kwargs)[0]
+
+  def inverse(self, y, x=None, **kwargs):
+    return self.inverse_and_likelihood_contribution(y, x=x, **kwargs)[0]
+
+  # every layer is also usable on its own: a one-layer chain without the base log-prob
+  def _inverse_and_likelihood_contribution(self, y, x=None, **kwargs):
+    from surjectors_b200 import _runtime
+
+    return _runtime.run_transform(self, y, x, honour_x=True)
+
+  def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):
+    raise NotImplementedError(
+      f"{type(self).__name__}: the sampling (forward) direction is outside the log_prob hot path built here "
+      "(SURVEY.md section 8f)"
+    )
+
+  def _trace(self, d_in: int, dx: int):
+    """-> list[LayerSpec], d_out"""
+    raise NotImplementedError
+
+
+class Bijector(Surjector):
+  """surjectors/_src/bijectors/bijector.py:9-40."""
+
+  def inverse_and_log_det(self, y, x=None, **kwargs):
+    return self.inverse_and_likelihood_contribution(y, x=x, **kwargs)
+
+  def forward_and_log_det(self, z, x=None, **kwargs):
+    return self.forward_and_likelihood_contribution(z, x=x, **kwargs)
+
+
+class Chain(Surjector):
+  """surjectors/_src/surjectors/chain.py:22-67: left fold over the layers, summing contributions;
+  the same `x` goes to every Surjector layer."""
+
+  def __init__(self, transforms):
+    self._transforms = transforms
+
+  def _trace(self, d_in, dx):
+    specs, d = [], d_in
+    for t in self._transforms:
+      if not isinstance(t, Surjector):
+        raise _sym.Unsupported(f"Chain element {type(t).__name__} is not a surjectors_b200 layer")
+      s, d = t._trace(d, dx)
+      specs.extend(s)
+    return specs, d
+
+
+# ------------------------------------------------------------------ bijectors
+def _decode_inner(bij, theta, n_dims, what):
+  m = _sym.match_rqs(bij, theta, n_dims)
+  if m is not None:
+    inner, n_bins, lo, hi = m
+    return dict(inner=inner, layout=_abi.LAYOUT_INTERLEAVED, n_bins=n_bins, range_min=lo, range_max=hi)
+  m = _sym.match_affine(bij, theta, n_dims)
+  if m is not None:
+    return dict(inner=m[0], layout=m[1])
+  raise _sym.Unsupported(
+    f"{what}: bijector_fn returned {type(bij).__name__}; supported inner bijectors are ScalarAffine, "
+    "RationalQuadraticSpline and Inverse(...) of those"
+  )
+
+
+class MaskedCoupling(Bijector):
+  """surjectors/_src/bijectors/masked_coupling.py:12-85 (over distrax.MaskedCoupling).
+
+  mask True = the dimension passes through unchanged and is visible to the conditioner."""
+
+  def __init__(self, mask, conditioner, bijector_fn, event_ndims=None, inner_event_ndims=0):
+    mask = mask.cpu().numpy() if _is_array(mask) else np.asarray(mask)
+    if mask.dtype != bool:
+      raise ValueError(f"`mask` must have values of type `bool`; got values of type `{mask.dtype}`.")
+    if event_ndims is not None and event_ndims < inner_event_ndims:
+      raise ValueError(f"`event_ndims={event_ndims}` should be at least as large as "
+                       f"`inner_event_ndims={inner_event_ndims}`.")
+    if mask.ndim != 1 or inner_event_ndims != 0 or event_ndims not in (None, 1):
+      raise _sym.Unsupported("MaskedCoupling: only 1-d masks with scalar inner bijectors are implemented")
+    self._mask = mask
+    self._conditioner = conditioner
+    self._inner_bijector = bijector_fn
+    self._event_ndims = 1
+    self._inner_event_ndims = 0
+
+  @property
+  def mask(self):
+    return self._mask
+
+  def _trace(self, d_in, dx):
+    if self._mask.shape != (d_in,):
+      raise ValueError(f"mask of shape {self._mask.shape} does not match an event of {d_in} dims")
+    src = _sym.InputSym(d_in + dx)
+    theta = self._conditioner(src)
+    if not isinstance(theta, _sym.NetSym) or theta.source is not src:
+      raise _sym.Unsupported("conditioner must be a make_mlp / hk.nets.MLP / hk.Linear stack on its input")
+    inner = _decode_inner(self._inner_bijector(theta), theta, d_in, type(self).__name__)
+    spec = LayerSpec(kind=_abi.LAYER_COUPLING, dim_in=d_in, dim_out=d_in, use_x=dx > 0, mask=self._mask.copy(),
+                     conditioner=_mlp_spec(theta), **inner)
+    return [spec], d_in
+
+
+class AffineMaskedCoupling(MaskedCoupling):
+  """surjectors/_src/bijectors/affine_masked_coupling.py:39-52."""
+
+  def __init__(self, mask, conditioner, event_ndims=None, inner_event_ndims=0):
+    def _bijector_fn(params):
+      means, log_scales = _sym.split(params, 2, -1)
+      return _sym.ScalarAffine(means, _sym.exp(log_scales))
+
+    super().__init__(mask, conditioner, _bijector_fn, event_ndims, inner_event_ndims)
+
+
+class RationalQuadraticSplineMaskedCoupling(MaskedCoupling):
+  """surjectors/_src/bijectors/rq_masked_coupling.py:33-65."""
+
+  def __init__(self, mask, conditioner, range_min, range_max, event_ndims=None, inner_event_ndims=0):
+    self.range_min = range_min
+    self.range_max = range_max
+
+    def _bijector_fn(params):
+      return _sym.RationalQuadraticSpline(params, self.range_min, self.range_max)
+
+    super().__init__(mask, conditioner, _bijector_fn, event_ndims, inner_event_ndims)
+
+
+class MaskedAutoregressive(Bijector):
+  """surjectors/_src/bijectors/masked_autoregressive.py:11-79."""
+
+  def __init__(self, conditioner, bijector_fn, event_ndims=1, inner_event_ndims=0):
+    from surjectors_b200.nn import MADE
+
+    if event_ndims is not None and event_ndims < inner_event_ndims:
+      raise ValueError(f"`event_ndims={event_ndims}` should be at least as large as "
+                       f"`inner_event_ndims={inner_event_ndims}`.")
+    if not isinstance(conditioner, MADE):
+      raise ValueError("conditioner should be a MADE when used MaskedAutoregressive flow")
+    if event_ndims != 1 or inner_event_ndims != 0:
+      raise _sym.Unsupported("MaskedAutoregressive: only event_ndims=1, inner_event_ndims=0 is implemented")
+    self._event_ndims = event_ndims
+    self._inner_event_ndims = inner_event_ndims
+    self.conditioner = conditioner
+    self._inner_bijector = bijector_fn
+
+  def _trace_made(self, d, ctx):
+    y_sym = _sym.InputSym(d)
+    c_sym = _sym.InputSym(ctx) if ctx > 0 else None
+    theta = self.conditioner(y_sym, c_sym)
+    if not isinstance(theta, _sym.MadeSym):
+      raise _sym.Unsupported("MADE conditioner returned an unexpected object")
+    inner = _decode_inner(self._inner_bijector(theta), theta, d, type(self).__name__)
+    return theta.spec, inner
+
+  def _trace(self, d_in, dx):
+    made, inner = self._trace_made(d_in, dx)
+    spec = LayerSpec(kind=_abi.LAYER_MAF, dim_in=d_in, dim_out=d_in, use_x=dx > 0, made=made, **inner)
+    return [spec], d_in
+
+
+class AffineMaskedAutoregressive(MaskedAutoregressive):
+  """surjectors/_src/bijectors/affine_masked_autoregressive.py:48-58."""
+
+  def __init__(self, conditioner, event_ndims=1, inner_event_ndims=0):
+    def bijector_fn(params):
+      means, log_scales = _sym.unstack(params, -1)
+      return _sym.ScalarAffine(means, _sym.exp(log_scales))
+
+    super().__init__(conditioner, bijector_fn, event_ndims, inner_event_ndims)
+
+
+class LULinear(Bijector, hk.Module):
+  """surjectors/_src/bijectors/lu_linear.py:11-93: z = (y @ U) @ L, lc = sum(log(softplus(d) + 1e-4))."""
+
+  def __init__(self, n_dimension, with_bias=False, dtype=None):
+    hk.Module.__init__(self)
+    if with_bias:
+      raise NotImplementedError()
+    if dtype not in (None, torch.float32, np.float32, "float32"):
+      raise _sym.Unsupported("LULinear: only float32 is implemented")
+    self.n_dimension = int(n_dimension)
+    n_tri = ((self.n_dimension - 1) * self.n_dimension) // 2
+    self._lower = hk.get_parameter("lower_entries", [n_tri], init=hk.zeros)
+    self._upper = hk.get_parameter("upper_entries", [n_tri], init=hk.zeros)
+    self._diag = hk.get_parameter("diag_entries", [self.n_dimension], init=hk.ones)
+
+  def _trace(self, d_in, dx):
+    if d_in != self.n_dimension:
+      raise ValueError(f"LULinear({self.n_dimension}) applied to an event of {d_in} dims")
+    spec = LayerSpec(kind=_abi.LAYER_LU, dim_in=d_in, dim_out=d_in, lu=(self._lower, self._upper, self._diag))
+    return [spec], d_in
+
+  def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):  # lu_linear.py:92-93
+    raise NotImplementedError()
+
+
+class Permutation(Bijector):
+  """surjectors/_src/bijectors/permutation.py:7-37."""
+
+  def __init__(self, permutation, event_ndims_in):
+    p = permutation.cpu().numpy() if _is_array(permutation) else np.asarray(permutation)
+    self.permutation = p.astype(np.int32)
+    self.event_ndims_in = event_ndims_in
+    if event_ndims_in != 1 or self.permutation.ndim != 1:
+      raise _sym.Unsupported("Permutation: only vector events are implemented")
+
+  def _trace(self, d_in, dx):
+    if self.permutation.shape != (d_in,):
+      raise ValueError(f"permutation of length {self.permutation.size} applied to an event of {d_in} dims")
+    return [LayerSpec(kind=_abi.LAYER_PERMUTATION, dim_in=d_in, dim_out=d_in, permutation=self.permutation.copy())], d_in
+
+
+# ------------------------------------------------------------------ surjectors
+def _trace_decoder(decoder, k, dx, n_out):
+  src = _sym.InputSym(k + dx)
+  net = _sym.match_normal_decoder(decoder(src), src, n_out)
+  return _mlp_spec(net)
+
+
+class Slice(Surjector):
+  """surjectors/_src/surjectors/slice.py:8-78."""
+
+  def __init__(self, n_keep, decoder):
+    self.n_keep = int(n_keep)
+    self.decoder = decoder
+
+  def _trace(self, d_in, dx):
+    k = self.n_keep
+    if not 0 < k < d_in:
+      raise ValueError(f"n_keep={k} must be in (0, {d_in})")
+    spec = LayerSpec(kind=_abi.LAYER_SLICE, dim_in=d_in, dim_out=k, use_x=dx > 0,
+                     decoder=_trace_decoder(self.decoder, k, dx, d_in - k))
+    return [spec], k
+
+
+class MaskedCouplingInferenceFunnel(Surjector):
+  """surjectors/_src/surjectors/masked_coupling_inference_funnel.py:9-106."""
+
+  def __init__(self, n_keep, decoder, conditioner, bijector_fn):
+    self.n_keep = int(n_keep)
+    self.decoder = decoder
+    self.conditioner = conditioner
+    self.bijector_fn = bijector_fn
+
+  def _trace(self, d_in, dx):
+    k = self.n_keep
+    if not 0 < k < d_in:
+      raise ValueError(f"n_keep={k} must be in (0, {d_in})")
+    mask = np.arange(d_in) >= k  # :72-75
+    (cpl,), _ = MaskedCoupling(mask, self.conditioner, self.bijector_fn)._trace(d_in, dx)
+    cpl.kind = _abi.LAYER_COUPLING_FUNNEL
+    cpl.dim_out = k
+    cpl.mask = None
+    cpl.decoder = _trace_decoder(self.decoder, k, dx, d_in - k)
+    return [cpl], k
+
+
+class AffineMaskedCouplingInferenceFunnel(MaskedCouplingInferenceFunnel):
+  """surjectors/_src/surjectors/affine_masked_coupling_inference_funnel.py:11-55."""
+
+  def __init__(self, n_keep, decoder, conditioner):
+    def bijector_fn(params):
+      shift, log_scale = _sym.split(params, 2, -1)
+      return _sym.ScalarAffine(shift, _sym.exp(log_scale))
+
+    super().__init__(n_keep, decoder, conditioner, bijector_fn)
+
+
+class RationalQuadraticSplineMaskedCouplingInferenceFunnel(MaskedCouplingInferenceFunnel):
+  """surjectors/_src/surjectors/rq_masked_coupling_inference_funnel.py:11-86."""
+
+  def __init__(self, n_keep, decoder, conditioner, range_min, range_max):
+    self.range_min = range_min
+    self.range_max = range_max
+
+    def _bijector_fn(params):
+      return _sym.RationalQuadraticSpline(params, self.range_min, self.range_max)
+
+    super().__init__(n_keep, decoder, conditioner, _bijector_fn)
+
+
+class MaskedAutoregressiveInferenceFunnel(Surjector):
+  """surjectors/_src/surjectors/masked_autoregressive_inference_funnel.py:10-108."""
+
+  def __init__(self, n_keep, decoder, conditioner, bijector_fn):
+    self.n_keep = int(n_keep)
+    self.decoder = decoder
+    self.conditioner = conditioner
+    self.bijector_fn = bijector_fn
+
+  def _trace(self, d_in, dx):
+    k = self.n_keep
+    if not 0 < k < d_in:
+      raise ValueError(f"n_keep={k} must be in (0, {d_in})")
+    maf = MaskedAutoregressive(self.conditioner, self.bijector_fn)
+    made, inner = maf._trace_made(k, d_in - k + dx)
+    spec = LayerSpec(kind=_abi.LAYER_MAF_FUNNEL, dim_in=d_in, dim_out=k, use_x=dx > 0, made=made,
+                     decoder=_trace_decoder(self.decoder, k, dx, d_in - k), **inner)
+    return [spec], k
+
+
+class AffineMaskedAutoregressiveInferenceFunnel(MaskedAutoregressiveInferenceFunnel):
+  """surjectors/_src/surjectors/affine_masked_autoregressive_inference_funnel.py:13-65."""
+
+  def __init__(self, n_keep, decoder, conditioner):
+    def bijector_fn(params):
+      shift, log_scale = _sym.unstack(params, axis=-1)
+      return _sym.ScalarAffine(shift, _sym.exp(log_scale))
+
+    super().__init__(n_keep, decoder, conditioner, bijector_fn)
+
+
+# ----------------------------------------------------------------------- driver
+def trace_chain(transform, d_in, dx, honour_x=True) -> ChainSpec:
+  """Turn a transform into a ChainSpec inside the current hk frame."""
+  fr = hk.current_frame()
+  use_dx = dx if honour_x else 0
+  specs, _ = transform._trace(d_in, use_dx)
+  return ChainSpec(specs, d_in, use_dx, fr.layout)
+
+
+class TransformedDistribution:
+  """surjectors/_src/distributions/transformed_distribution.py:12-139 (log_prob direction)."""
+
+  def __init__(self, base_distribution, transform):
+    self.base_distribution = base_distribution
+    self.transform = transform
+
+  def __call__(self, method, **kwargs):
+    return getattr(self, method)(**kwargs)
+
+  def log_prob(self, y, x=None):
+    _, lp = self.inverse_and_log_prob(y, x)
+    return lp
+
+  def inverse_and_log_prob(self, y, x=None):
+    from surjectors_b200 import _runtime
+
+    if x is not None:  # :83-85 (chex.assert_equal_rank / assert_axis_dimension)
+      if y.dim() != x.dim():
+        raise AssertionError(f"[Chex] Arrays have different rank: {y.dim()} vs {x.dim()}")
+      if y.shape[0] != x.shape[0]:
+        raise AssertionError(f"[Chex] batch axis mismatch: {y.shape[0]} vs {x.shape[0]}")
+    # quirk Q1 (:87-88): distrax.Bijector instances are called WITHOUT x
+    honour_x = not isinstance(self.transform, MaskedCoupling)
+    return _runtime.run_transform(self.transform, y, x, honour_x=honour_x, base=self.base_distribution)
+
+  def sample(self, sample_shape=(), x=None):
+    raise NotImplementedError("sampling is outside the log_prob hot path built here (SURVEY.md section 8f)")
+
+  def sample_and_log_prob(self, sample_shape=(), x=None):
+    raise NotImplementedError("sampling is outside the log_prob hot path built here (SURVEY.md section 8f)")

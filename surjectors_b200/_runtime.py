@@ -1,0 +1,226 @@
+"""Plans, launches and autograd glue above the C ABI (include/surj_b200.h).
+
+torch is used for what the prompt calls plumbing: device memory, the current CUDA stream and
+autograd bookkeeping (`torch.autograd.Function` plays the role `jax.custom_vjp` around a
+`jax.ffi.ffi_call` would play in the reference).  All arithmetic is in libsurj_b200.so; there is
+no CPU or eager path -- a call on CPU tensors, or with the library missing, raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import torch
+
+from surjectors_b200 import _abi, _sym, hk
+from surjectors_b200._spec import ChainSpec
+
+BASE_STANDARD_NORMAL, BASE_NONE = 0, 1
+
+_plans = {}
+_plans_lock = threading.Lock()
+
+
+class Plan:
+  """Owns a `SurjPlan*`: the compiled description of one chain (what jax.jit's trace cache holds)."""
+
+  def __init__(self, spec: ChainSpec, base=BASE_STANDARD_NORMAL, mode=_abi.MODE_AUTO):
+    lib = _abi.lib()
+    arr, keep = spec.to_c()
+    handle = C.c_void_p()
+    st = lib.surj_plan_create(arr, len(spec.layers), spec.dim_in, spec.dim_x, spec.n_params, mode, base,
+                              C.byref(handle))
+    del keep
+    _abi.check(st, "surj_plan_create")
+    self._lib = lib
+    self._h = handle
+    self.spec = spec
+    self.base = base
+    self.dim_in, self.dim_x, self.dim_out, self.n_params = spec.dim_in, spec.dim_x, spec.dim_out, spec.n_params
+    self.is_fused = bool(lib.surj_plan_is_fused(handle))
+    self.key = int(lib.surj_plan_key(handle))
+    self._ws = {}
+
+  def __del__(self):
+    h, self._h = getattr(self, "_h", None), None
+    if h:
+      try:
+        self._lib.surj_plan_destroy(h)
+      except Exception:  # noqa: BLE001  (interpreter shutdown)
+        pass
+
+  def launches(self, backward=False):
+    return int(self._lib.surj_plan_launches(self._h, int(backward)))
+
+  def workspace(self, batch, backward, device):
+    """Cached scratch buffer (the caller of the C ABI owns all device memory)."""
+    n = int(self._lib.surj_plan_workspace_bytes(self._h, batch, int(backward)))
+    key = (batch, bool(backward), str(device))
+    buf = self._ws.get(key)
+    if buf is None or buf.numel() < n:
+      buf = torch.empty(max(n, 16), dtype=torch.uint8, device=device)
+      self._ws[key] = buf
+    return buf, n
+
+  # -- raw launches on the current stream; all arguments are contiguous float32 CUDA tensors
+  def fwd(self, y, x, flat, want_z=True, lp_out=None, z_out=None):
+    B = y.shape[0]
+    _check_inputs(self, y, x, flat)
+    lp = lp_out if lp_out is not None else torch.empty(B, dtype=torch.float32, device=y.device)
+    z = z_out
+    if z is None and want_z:
+      z = torch.empty((B, self.dim_out), dtype=torch.float32, device=y.device)
+    if B == 0:
+      return z, lp
+    ws, n = self.workspace(B, False, y.device)
+    st = self._lib.surj_chain_logprob_fwd(
+      self._h, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), _ptr(z), lp.data_ptr(), ws.data_ptr(), n, B)
+    _abi.check(st, "surj_chain_logprob_fwd")
+    return z, lp
+
+  def bwd(self, y, x, flat, g_lp=None, g_scale=1.0, g_z=None, want_gy=False, want_gx=False, want_lp=False,
+          g_params=None, loss_out=None):
+    B = y.shape[0]
+    _check_inputs(self, y, x, flat)
+    dev = y.device
+    gp = g_params if g_params is not None else torch.empty(self.n_params, dtype=torch.float32, device=dev)
+    gy = torch.empty_like(y) if want_gy else None
+    gx = torch.empty_like(x) if (want_gx and x is not None) else None
+    lp = torch.empty(B, dtype=torch.float32, device=dev) if want_lp else None
+    if B == 0:
+      gp.zero_()
+      return gp, gy, gx, lp
+    ws, n = self.workspace(B, True, dev)
+    st = self._lib.surj_chain_logprob_bwd(
+      self._h, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), _ptr(g_lp), float(g_scale), _ptr(g_z),
+      gp.data_ptr(), _ptr(loss_out), _ptr(lp), _ptr(gy), _ptr(gx), ws.data_ptr(), n, B)
+    _abi.check(st, "surj_chain_logprob_bwd")
+    return gp, gy, gx, lp
+
+
+def _ptr(t):
+  return None if t is None else t.data_ptr()
+
+
+def _stream(t):
+  return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_inputs(plan, y, x, flat):
+  if not y.is_cuda:
+    raise _abi.SurjError("surjectors_b200 computes on CUDA tensors only (there is no CPU fallback)")
+  if y.dim() != 2 or y.shape[1] != plan.dim_in or y.dtype != torch.float32 or not y.is_contiguous():
+    raise ValueError(f"y must be a contiguous float32 [B, {plan.dim_in}] tensor, got {tuple(y.shape)} {y.dtype}")
+  if plan.dim_x > 0:
+    if x is None or x.dim() != 2 or x.shape != (y.shape[0], plan.dim_x) or x.dtype != torch.float32 \
+        or not x.is_contiguous() or x.device != y.device:
+      raise ValueError(f"x must be a contiguous float32 [B, {plan.dim_x}] tensor on the device of y")
+  if flat.numel() != plan.n_params or flat.dtype != torch.float32 or flat.device != y.device \
+      or not flat.is_contiguous():
+    raise ValueError("flat parameter buffer does not match the plan")
+
+
+def get_plan(spec: ChainSpec, base=BASE_STANDARD_NORMAL, mode=_abi.MODE_AUTO) -> Plan:
+  key = (spec.structure(), base, mode)
+  with _plans_lock:
+    plan = _plans.get(key)
+    if plan is None:
+      plan = Plan(spec, base, mode)
+      _plans[key] = plan
+    return plan
+
+
+class _LogProbFn(torch.autograd.Function):
+  """(y, x, flat) -> (z, lp) with the hand-written VJP kernel as backward."""
+
+  @staticmethod
+  def forward(ctx, plan, y, x, flat):
+    z, lp = plan.fwd(y, x, flat, want_z=True)
+    ctx.plan = plan
+    ctx.save_for_backward(y, x, flat)
+    return z, lp
+
+  @staticmethod
+  def backward(ctx, g_z, g_lp):
+    plan = ctx.plan
+    y, x, flat = ctx.saved_tensors
+    need_y, need_x = ctx.needs_input_grad[1], ctx.needs_input_grad[2] and x is not None
+    if g_lp is None:
+      g_lp = torch.zeros(y.shape[0], dtype=torch.float32, device=y.device)
+    g_lp = g_lp.contiguous()
+    if g_z is not None:
+      g_z = g_z.contiguous()
+    gp, gy, gx, _ = plan.bwd(y, x, flat, g_lp=g_lp, g_z=g_z, want_gy=need_y, want_gx=need_x)
+    return None, gy, gx, (gp if ctx.needs_input_grad[3] else None)
+
+
+def _prep(t, what):
+  if t is None:
+    return None
+  if not isinstance(t, torch.Tensor):
+    raise TypeError(f"{what} must be a torch tensor (device memory is managed through torch), got {type(t).__name__}")
+  if t.dtype != torch.float32:
+    t = t.to(torch.float32)
+  return t.contiguous()
+
+
+def run_transform(transform, y, x, honour_x=True, base=None):
+  """Trace `transform` in the current hk frame and run it: returns (z, lp-or-lc)."""
+  from surjectors_b200 import _layers
+
+  fr = hk.current_frame()
+  y = _prep(y, "y")
+  x = _prep(x, "x")
+  if y.dim() != 2:  # lu_linear.py:89 / funnels :87,90 index [:, :k]: the path is defined for [B, D]
+    raise ValueError(f"y must have shape [batch, event], got {tuple(y.shape)}")
+  dx = x.shape[-1] if (x is not None and honour_x) else 0
+  spec = _layers.trace_chain(transform, y.shape[-1], dx, honour_x=True)
+  if base is not None:
+    _sym.check_standard_normal_base(base, spec.dim_out)
+  if fr.is_init:
+    fr.device = y.device
+    B = y.shape[0]
+    return (torch.zeros((B, spec.dim_out), dtype=torch.float32, device=y.device),
+            torch.zeros(B, dtype=torch.float32, device=y.device))
+  if not y.is_cuda:
+    raise _abi.SurjError("surjectors_b200 computes on CUDA tensors only (there is no CPU fallback)")
+  plan = get_plan(spec, BASE_STANDARD_NORMAL if base is not None else BASE_NONE)
+  flat = hk.pack_params(fr.params, fr.layout, y.device)
+  xx = x if dx > 0 else None
+  if torch.is_grad_enabled() and (flat.requires_grad or y.requires_grad or (xx is not None and xx.requires_grad)):
+    return _LogProbFn.apply(plan, y, xx, flat)
+  return plan.fwd(y, xx, flat, want_z=True)
+
+
+def value_and_grad(fun, has_aux=False):
+  """`jax.value_and_grad(fun)` for loss functions of a params tree built from `model.apply`
+  (examples/coupling_inference_surjection.py:83-87).  Gradients come from the VJP kernels."""
+
+  def wrapped(params, *args, **kwargs):
+    layout = getattr(params, "layout", None)
+    if layout is not None and isinstance(getattr(params, "flat", None), torch.Tensor):
+      leaf = params.flat.detach().requires_grad_(True)
+      tree = hk.tree_from_flat(leaf, layout)
+      with torch.enable_grad():
+        out = fun(tree, *args, **kwargs)
+        loss = out[0] if has_aux else out
+        (g,) = torch.autograd.grad(loss, [leaf], allow_unused=True)
+      if g is None:
+        g = torch.zeros_like(leaf)
+      grads = hk.tree_from_flat(g, layout)
+    else:
+      leaves = {m: {k: v.detach().requires_grad_(True) for k, v in b.items()} for m, b in params.items()}
+      with torch.enable_grad():
+        out = fun(leaves, *args, **kwargs)
+        loss = out[0] if has_aux else out
+        flat = [v for b in leaves.values() for v in b.values()]
+        gs = torch.autograd.grad(loss, flat, allow_unused=True)
+      it = iter(gs)
+      grads = {m: {k: (lambda g, v: torch.zeros_like(v) if g is None else g)(next(it), v) for k, v in b.items()}
+               for m, b in leaves.items()}
+    if has_aux:
+      return (loss.detach(), out[1]), grads
+    return loss.detach(), grads
+
+  return wrapped

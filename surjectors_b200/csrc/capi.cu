@@ -1,0 +1,508 @@
+// C ABI (include/surj_b200.h): plan construction/validation, dispatch to the fused whole-chain
+// kernels (chain.cuh, registered per chain) or the per-layer path (layered.cu), gradient
+// reduction and the fused Adam update.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "plan.h"
+
+// ------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+void surj_set_error(const std::string& msg) { g_err = msg; }
+int surj_cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return SURJ_E_CUDA;
+}
+extern "C" const char* surj_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t surj_abi_version(void) { return SURJ_ABI_VERSION; }
+
+// ---------------------------------------------------------------------- registry
+namespace {
+struct RegEntry {
+  SmallKernels k;
+  std::string name;
+};
+std::map<unsigned long long, RegEntry>& registry() {
+  static std::map<unsigned long long, RegEntry> r;
+  return r;
+}
+std::mutex& reg_mutex() {
+  static std::mutex m;
+  return m;
+}
+}  // namespace
+
+void surj_register_small(unsigned long long key, SmallKernels k, const char* name) {
+  std::lock_guard<std::mutex> g(reg_mutex());
+  RegEntry e;
+  e.k = k;
+  e.name = name;
+  registry()[key] = e;
+}
+const SmallKernels* surj_find_small(unsigned long long key) {
+  std::lock_guard<std::mutex> g(reg_mutex());
+  auto it = registry().find(key);
+  return it == registry().end() ? nullptr : &it->second.k;
+}
+int surj_registry_count() { return (int)registry().size(); }
+extern "C" int32_t surj_registry_size(void) { return surj_registry_count(); }
+
+// ----------------------------------------------------------------------- helpers
+extern "C" int64_t surj_made_masks(int32_t n_params, int32_t input_size, const int32_t* hidden, int32_t n_hidden,
+                                   uint8_t* out) {
+  // TFP _make_dense_autoregressive_masks (input_order='left-to-right', hidden_degrees='equal'),
+  // called by the reference at surjectors/_src/conditioners/nn/made.py:54-56.
+  if (input_size <= 0 || n_params <= 0 || n_hidden < 0 || n_hidden > SURJ_MAX_NET_LAYERS) return SURJ_E_INVALID;
+  std::vector<std::vector<int>> deg;
+  deg.emplace_back();
+  for (int d = 1; d <= input_size; ++d) deg[0].push_back(d);
+  for (int l = 0; l < n_hidden; ++l) {
+    const int units = hidden[l];
+    if (units <= 0) return SURJ_E_INVALID;
+    int mn = deg.back()[0];
+    for (int v : deg.back()) mn = v < mn ? v : mn;
+    mn = mn < input_size - 1 ? mn : input_size - 1;
+    std::vector<int> d(units);
+    for (int u = 1; u <= units; ++u) {
+      // ceil(u * (D - 1) / (units + 1)) evaluated like numpy: float64 division then ceil
+      const int c = (int)std::ceil((double)(u * (input_size - 1)) / (double)(units + 1));
+      d[u - 1] = c > mn ? c : mn;
+    }
+    deg.push_back(d);
+  }
+  int64_t total = 0;
+  for (int l = 0; l <= n_hidden; ++l) {
+    const int rows = (int)deg[l].size();
+    const int cols = l < n_hidden ? (int)deg[l + 1].size() : input_size * n_params;
+    if (out) {
+      for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < cols; ++j) {
+          uint8_t m;
+          if (l < n_hidden) m = deg[l][i] <= deg[l + 1][j];
+          else m = deg[l][i] < deg[0][j / n_params];
+          out[total + (int64_t)i * cols + j] = m;
+        }
+    }
+    total += (int64_t)rows * cols;
+  }
+  return total;
+}
+
+extern "C" int surj_permutation_inverse(const int32_t* permutation, int32_t n, int32_t* inverse_out) {
+  // permutation.py:31-36: zeros(size, int).at[perm].set(arange(size))
+  if (!permutation || !inverse_out || n <= 0) return SURJ_E_INVALID;
+  for (int i = 0; i < n; ++i) inverse_out[i] = 0;
+  for (int i = 0; i < n; ++i) {
+    if (permutation[i] < 0 || permutation[i] >= n) {
+      surj_set_error("permutation entry out of range");
+      return SURJ_E_INVALID;
+    }
+    inverse_out[permutation[i]] = i;
+  }
+  return SURJ_OK;
+}
+
+// ------------------------------------------------------------------- validation
+static int check_mlp(const SurjMlpDesc& m, int in_w, int out_w, int64_t np, const char* what) {
+  char buf[256];
+  if (m.n_layers <= 0 || m.n_layers > SURJ_MAX_NET_LAYERS) {
+    snprintf(buf, sizeof buf, "%s: n_layers=%d out of range", what, m.n_layers);
+    surj_set_error(buf);
+    return SURJ_E_INVALID;
+  }
+  if (m.widths[0] != in_w || m.widths[m.n_layers] != out_w) {
+    snprintf(buf, sizeof buf, "%s: expected %d -> %d, descriptor says %d -> %d", what, in_w, out_w, m.widths[0],
+             m.widths[m.n_layers]);
+    surj_set_error(buf);
+    return SURJ_E_INVALID;
+  }
+  for (int l = 0; l < m.n_layers; ++l) {
+    const int64_t wsz = (int64_t)m.widths[l] * m.widths[l + 1];
+    if (m.widths[l] <= 0 || m.widths[l + 1] <= 0 || m.w_off[l] < 0 || m.w_off[l] + wsz > np ||
+        (m.b_off[l] >= 0 && m.b_off[l] + m.widths[l + 1] > np) || m.act[l] < 0 || m.act[l] > SURJ_ACT_LEAKY_RELU) {
+      snprintf(buf, sizeof buf, "%s: layer %d has bad width / offset / activation", what, l);
+      surj_set_error(buf);
+      return SURJ_E_INVALID;
+    }
+  }
+  return SURJ_OK;
+}
+
+static int check_made(const SurjMadeDesc& m, int in_w, int n_par, int ctx, int64_t np, const char* what) {
+  char buf[256];
+  if (m.input_size != in_w || m.n_params != n_par || m.ctx_dim != ctx || m.n_hidden < 1 ||
+      m.n_hidden > SURJ_MAX_NET_LAYERS || m.act < 0 || m.act > SURJ_ACT_LEAKY_RELU) {
+    snprintf(buf, sizeof buf, "%s: MADE(input=%d, params=%d, ctx=%d, hidden layers=%d) does not fit layer (%d, %d, %d)",
+             what, m.input_size, m.n_params, m.ctx_dim, m.n_hidden, in_w, n_par, ctx);
+    surj_set_error(buf);
+    return SURJ_E_INVALID;
+  }
+  int prev = in_w;
+  for (int l = 0; l <= m.n_hidden; ++l) {
+    const int cur = l < m.n_hidden ? m.hidden[l] : in_w * n_par;
+    if (cur <= 0 || m.w_off[l] < 0 || m.w_off[l] + (int64_t)prev * cur > np || m.b_off[l] < 0 ||
+        m.b_off[l] + cur > np) {
+      snprintf(buf, sizeof buf, "%s: masked layer %d has bad width / offset", what, l);
+      surj_set_error(buf);
+      return SURJ_E_INVALID;
+    }
+    prev = cur;
+  }
+  if (ctx > 0 && (m.ctx_w_off < 0 || m.ctx_w_off + (int64_t)ctx * m.hidden[0] > np || m.ctx_b_off < 0 ||
+                  m.ctx_b_off + m.hidden[0] > np)) {
+    surj_set_error(std::string(what) + ": context Linear offsets out of range");
+    return SURJ_E_INVALID;
+  }
+  return SURJ_OK;
+}
+
+static int inner_params(const SurjLayerDesc& L) {
+  if (L.inner == SURJ_INNER_AFFINE || L.inner == SURJ_INNER_AFFINE_INV) return 2;
+  return 3 * L.n_bins + 1;
+}
+
+static int validate_layer(const SurjLayerDesc& L, int k, int d_in, int dim_x, int64_t np) {
+  char what[64];
+  snprintf(what, sizeof what, "layer %d", k);
+  char buf[256];
+  if (L.dim_in != d_in) {
+    snprintf(buf, sizeof buf, "%s: dim_in=%d but the chain delivers %d", what, L.dim_in, d_in);
+    surj_set_error(buf);
+    return SURJ_E_INVALID;
+  }
+  if (L.use_x && dim_x <= 0) {
+    surj_set_error(std::string(what) + ": use_x set but the chain has no x");
+    return SURJ_E_INVALID;
+  }
+  const int dx = L.use_x ? dim_x : 0;
+  const bool funnel =
+      L.kind == SURJ_LAYER_COUPLING_FUNNEL || L.kind == SURJ_LAYER_MAF_FUNNEL || L.kind == SURJ_LAYER_SLICE;
+  if (funnel) {
+    if (L.dim_out <= 0 || L.dim_out >= L.dim_in) {
+      snprintf(buf, sizeof buf, "%s: n_keep=%d must be in (0, %d)", what, L.dim_out, L.dim_in);
+      surj_set_error(buf);
+      return SURJ_E_INVALID;
+    }
+    int r = check_mlp(L.decoder, L.dim_out + dx, 2 * (L.dim_in - L.dim_out), np, "decoder");
+    if (r) return r;
+  } else if (L.dim_out != L.dim_in) {
+    surj_set_error(std::string(what) + ": bijector must keep the width");
+    return SURJ_E_INVALID;
+  }
+  const bool has_inner = L.kind == SURJ_LAYER_COUPLING || L.kind == SURJ_LAYER_COUPLING_FUNNEL ||
+                         L.kind == SURJ_LAYER_MAF || L.kind == SURJ_LAYER_MAF_FUNNEL;
+  if (has_inner) {
+    if (L.inner < SURJ_INNER_AFFINE || L.inner > SURJ_INNER_RQS_INV) {
+      surj_set_error(std::string(what) + ": unknown inner bijector");
+      return SURJ_E_UNSUPPORTED;
+    }
+    if (L.inner >= SURJ_INNER_RQS) {
+      if (L.n_bins < 1 || !(L.range_max > L.range_min) || L.n_bins * 1e-4f > L.range_max - L.range_min) {
+        surj_set_error(std::string(what) + ": bad spline bins / range");
+        return SURJ_E_INVALID;
+      }
+    }
+  }
+  switch (L.kind) {
+    case SURJ_LAYER_COUPLING: {
+      if (!L.mask) {
+        surj_set_error(std::string(what) + ": coupling needs a mask");
+        return SURJ_E_INVALID;
+      }
+      return check_mlp(L.conditioner, L.dim_in + dx, L.dim_in * inner_params(L), np, "conditioner");
+    }
+    case SURJ_LAYER_COUPLING_FUNNEL:
+      return check_mlp(L.conditioner, L.dim_in + dx, L.dim_in * inner_params(L), np, "conditioner");
+    case SURJ_LAYER_MAF:
+      return check_made(L.made, L.dim_in, inner_params(L), dx, np, "MADE");
+    case SURJ_LAYER_MAF_FUNNEL:
+      return check_made(L.made, L.dim_out, inner_params(L), L.dim_in - L.dim_out + dx, np, "MADE");
+    case SURJ_LAYER_SLICE:
+      return SURJ_OK;
+    case SURJ_LAYER_LU: {
+      const int64_t n = L.dim_in, tri = n * (n - 1) / 2;
+      if (L.lu_lower_off < 0 || L.lu_lower_off + tri > np || L.lu_upper_off < 0 || L.lu_upper_off + tri > np ||
+          L.lu_diag_off < 0 || L.lu_diag_off + n > np) {
+        surj_set_error(std::string(what) + ": LULinear offsets out of range");
+        return SURJ_E_INVALID;
+      }
+      return SURJ_OK;
+    }
+    case SURJ_LAYER_PERMUTATION: {
+      if (!L.permutation) {
+        surj_set_error(std::string(what) + ": permutation missing");
+        return SURJ_E_INVALID;
+      }
+      std::vector<char> seen(L.dim_in, 0);
+      for (int d = 0; d < L.dim_in; ++d) {
+        const int p = L.permutation[d];
+        if (p < 0 || p >= L.dim_in || seen[p]) {
+          surj_set_error(std::string(what) + ": not a permutation");
+          return SURJ_E_INVALID;
+        }
+        seen[p] = 1;
+      }
+      return SURJ_OK;
+    }
+    default:
+      surj_set_error(std::string(what) + ": unknown layer kind");
+      return SURJ_E_UNSUPPORTED;
+  }
+}
+
+// -------------------------------------------------------------------------- plan
+extern "C" int surj_plan_create(const SurjLayerDesc* layers, int32_t n_layers, int32_t dim_in, int32_t dim_x,
+                                int64_t n_params, int32_t mode, int32_t base, SurjPlan** out) {
+  if (!layers || !out || n_layers <= 0 || dim_in <= 0 || dim_x < 0 || n_params < 0 ||
+      (base != SURJ_BASE_STANDARD_NORMAL && base != SURJ_BASE_NONE)) {
+    surj_set_error("surj_plan_create: bad arguments");
+    return SURJ_E_INVALID;
+  }
+  int d = dim_in;
+  for (int k = 0; k < n_layers; ++k) {
+    int r = validate_layer(layers[k], k, d, dim_x, n_params);
+    if (r) return r;
+    d = layers[k].dim_out;
+  }
+  SurjPlan* p = new SurjPlan();
+  p->layers.assign(layers, layers + n_layers);
+  p->masks.resize(n_layers);
+  p->perms.resize(n_layers);
+  for (int k = 0; k < n_layers; ++k) {
+    SurjLayerDesc& L = p->layers[k];
+    if (L.mask) {
+      p->masks[k].assign(L.mask, L.mask + L.dim_in);
+      L.mask = p->masks[k].data();
+    }
+    if (L.permutation) {
+      p->perms[k].assign(L.permutation, L.permutation + L.dim_in);
+      L.permutation = p->perms[k].data();
+    }
+  }
+  p->dim_in = dim_in;
+  p->dim_x = dim_x;
+  p->dim_out = d;
+  p->n_params = n_params;
+  p->mode = mode;
+  p->base = base;
+  surj_chain_key(p->layers.data(), n_layers, dim_in, dim_x, n_params, &p->key);
+  if (mode != SURJ_MODE_LAYERED) p->fused = surj_find_small(p->key);
+  if (mode == SURJ_MODE_FUSED && !p->fused) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "no fused kernel compiled in for chain key 0x%016llx (%d registered)",
+             (unsigned long long)p->key, surj_registry_count());
+    surj_set_error(buf);
+    delete p;
+    return SURJ_E_UNSUPPORTED;
+  }
+  if (!p->fused) {
+    int r = surj_layered_create(p);
+    if (r) {
+      delete p;
+      return r;
+    }
+  }
+  *out = p;
+  return SURJ_OK;
+}
+
+extern "C" void surj_plan_destroy(SurjPlan* plan) {
+  if (!plan) return;
+  surj_layered_destroy(plan);
+  delete plan;
+}
+extern "C" uint64_t surj_plan_key(const SurjPlan* plan) { return plan ? plan->key : 0; }
+extern "C" int32_t surj_plan_is_fused(const SurjPlan* plan) { return plan && plan->fused ? 1 : 0; }
+extern "C" int32_t surj_plan_dim_out(const SurjPlan* plan) { return plan ? plan->dim_out : -1; }
+
+static int ensure_device(const SurjPlan* p) {
+  if (p->dev_ready) return SURJ_OK;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return surj_cuda_fail(e, "cudaGetDevice");
+  e = cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return surj_cuda_fail(e, "cudaDeviceGetAttribute");
+  if (p->fused) {
+    e = p->fused->prepare();
+    if (e != cudaSuccess) return surj_cuda_fail(e, "cudaFuncSetAttribute(fused chain)");
+    e = p->fused->occupancy(&p->fwd_blocks, &p->bwd_blocks);
+    if (e != cudaSuccess) return surj_cuda_fail(e, "occupancy(fused chain)");
+    if (p->fwd_blocks < 1 || p->bwd_blocks < 1) {
+      surj_set_error("fused chain kernel does not fit on an SM");
+      return SURJ_E_CUDA;
+    }
+  }
+  p->dev_ready = true;
+  return SURJ_OK;
+}
+
+static int fused_grid(const SurjPlan* p, int64_t B, bool backward) {
+  const int nt = p->fused->nt;
+  const int64_t tiles = (B + nt - 1) / nt;
+  const int64_t cap = (int64_t)p->n_sm * (backward ? p->bwd_blocks : p->fwd_blocks);
+  return (int)(tiles < cap ? tiles : cap);
+}
+static int fused_npad(const SurjPlan* p) { return (int)((p->n_params + 1 + 3) / 4 * 4); }
+
+extern "C" size_t surj_plan_workspace_bytes(const SurjPlan* plan, int64_t batch, int32_t backward) {
+  if (!plan || batch <= 0) return 0;
+  if (plan->fused) {
+    if (!backward) return 0;
+    int64_t rows;
+    if (ensure_device(plan) == SURJ_OK) rows = fused_grid(plan, batch, true);
+    else {  // no device yet: an upper bound of one partial row per possible CTA
+      const int64_t tiles = (batch + plan->fused->nt - 1) / plan->fused->nt;
+      rows = tiles < 4096 ? tiles : 4096;
+    }
+    return (size_t)rows * fused_npad(plan) * sizeof(float);
+  }
+  return surj_layered_workspace_bytes(plan, batch, backward);
+}
+
+extern "C" int32_t surj_plan_launches(const SurjPlan* plan, int32_t backward) {
+  if (!plan) return 0;
+  if (plan->fused) return backward ? 2 : 1;
+  return surj_layered_launches(plan, backward);
+}
+
+static int check_io(const SurjPlan* plan, const void* y, const void* x, const void* params, int64_t B) {
+  if (!plan || !y || !params || B <= 0 || (plan->dim_x > 0 && !x)) {
+    surj_set_error("null plan / buffer, non-positive batch, or x missing for a conditional chain");
+    return SURJ_E_INVALID;
+  }
+  if (((uintptr_t)y | (uintptr_t)x | (uintptr_t)params) & 15u) {
+    surj_set_error("device pointers must be 16-byte aligned");
+    return SURJ_E_INVALID;
+  }
+  return SURJ_OK;
+}
+
+extern "C" int surj_chain_logprob_fwd(const SurjPlan* plan, SurjStream stream, const float* y, const float* x,
+                                      const float* params, float* z_out, float* lp_out, void* workspace,
+                                      size_t workspace_bytes, int64_t batch) {
+  int r = check_io(plan, y, x, params, batch);
+  if (r) return r;
+  if (!lp_out) {
+    surj_set_error("lp_out is required");
+    return SURJ_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->fused) {
+    r = ensure_device(plan);
+    if (r) return r;
+    cudaError_t e = plan->fused->fwd(fused_grid(plan, batch, false), st, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params,
+                                     z_out, lp_out, batch);
+    if (e != cudaSuccess) return surj_cuda_fail(e, "chain_fwd_kernel launch");
+    return SURJ_OK;
+  }
+  return surj_layered_fwd(plan, st, y, x, params, z_out, lp_out, workspace, workspace_bytes, batch);
+}
+
+// grads[p] = sum_rows partials[row][p]; column np carries sum(lp) -> loss = scale * sum(lp)
+__global__ void __launch_bounds__(256)
+surj_reduce_partials_kernel(const float* __restrict__ partials, int nrows, int npad, int np,
+                            float* __restrict__ g_params, float* __restrict__ loss_out, float loss_scale) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  if (col <= np) {
+    int r = w;
+    for (; r + 24 < nrows; r += 32) {
+      a0 += partials[(size_t)r * npad + col];
+      a1 += partials[(size_t)(r + 8) * npad + col];
+      a2 += partials[(size_t)(r + 16) * npad + col];
+      a3 += partials[(size_t)(r + 24) * npad + col];
+    }
+    for (; r < nrows; r += 8) a0 += partials[(size_t)r * npad + col];
+  }
+  red[w][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (w == 0 && col <= np) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][lane];
+    if (col < np) g_params[col] = s;
+    else if (loss_out) *loss_out = loss_scale * s;
+  }
+}
+
+extern "C" int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, const float* y, const float* x,
+                                      const float* params, const float* g_lp, float g_scale, const float* g_z,
+                                      float* g_params, float* loss_out, float* lp_out, float* g_y, float* g_x,
+                                      void* workspace, size_t workspace_bytes, int64_t batch) {
+  int r = check_io(plan, y, x, params, batch);
+  if (r) return r;
+  if (!g_params) {
+    surj_set_error("g_params is required");
+    return SURJ_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->fused) {
+    r = ensure_device(plan);
+    if (r) return r;
+    const int grid = fused_grid(plan, batch, true);
+    const int npad = fused_npad(plan);
+    const size_t need = (size_t)grid * npad * sizeof(float);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15u)) {
+      surj_set_error("workspace too small or misaligned for the backward pass");
+      return SURJ_E_WORKSPACE;
+    }
+    float* partials = (float*)workspace;
+    cudaError_t e =
+        plan->fused->bwd(grid, st, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z, partials,
+                         npad, lp_out, nullptr, g_y, g_x, batch);
+    if (e != cudaSuccess) return surj_cuda_fail(e, "chain_bwd_kernel launch");
+    const int np = (int)plan->n_params;
+    surj_reduce_partials_kernel<<<(np + 1 + 31) / 32, 256, 0, st>>>(partials, grid, npad, np, g_params, loss_out,
+                                                                    g_lp ? 1.0f : g_scale);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return surj_cuda_fail(e, "reduce_partials launch");
+    return SURJ_OK;
+  }
+  return surj_layered_bwd(plan, st, y, x, params, g_lp, g_scale, g_z, g_params, loss_out, lp_out, g_y, g_x, workspace,
+                          workspace_bytes, batch);
+}
+
+// -------------------------------------------------------------------------- Adam
+// optax.adam: mu = b1 mu + (1-b1) g; nu = b2 nu + (1-b2) g^2; bias correction with t = count+1;
+// p -= lr * mu_hat / (sqrt(nu_hat) + eps).  (examples/coupling_inference_surjection.py:78,88-89)
+__global__ void __launch_bounds__(256)
+surj_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu,
+                 const int32_t* __restrict__ count, long long n, float lr, float b1, float b2, float eps,
+                 float gscale) {
+  const int t = *count + 1;
+  const float c1 = 1.0f / (1.0f - powf(b1, (float)t));
+  const float c2 = 1.0f / (1.0f - powf(b2, (float)t));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float m = b1 * mu[i] + (1.0f - b1) * gi;
+    const float v = b2 * nu[i] + (1.0f - b2) * gi * gi;
+    mu[i] = m;
+    nu[i] = v;
+    p[i] -= lr * (m * c1) / (sqrtf(v * c2) + eps);
+  }
+}
+// separate tiny kernel so every thread of the update sees the same count
+__global__ void surj_count_inc_kernel(int32_t* count) { *count += 1; }
+
+extern "C" int surj_adam_step(SurjStream stream, float* params, const float* grads, float* mu, float* nu,
+                              int32_t* count, int64_t n, float lr, float b1, float b2, float eps, float grad_scale) {
+  if (!params || !grads || !mu || !nu || !count || n <= 0) {
+    surj_set_error("surj_adam_step: bad arguments");
+    return SURJ_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  surj_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, mu, nu, count, n, lr, b1, b2, eps, grad_scale);
+  surj_count_inc_kernel<<<1, 1, 0, st>>>(count);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return surj_cuda_fail(e, "adam launch");
+  return SURJ_OK;
+}

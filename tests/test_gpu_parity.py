@@ -1,0 +1,25 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on seeded inputs."""
+
+import numpy as np
+import pytest
+import torch
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+@pytest.mark.parametrize("batch", [1, 37, 1000])
+def test_fused_small_configs(name, batch):
+  out = parity.check_config(name, batch=batch, check_grad=True)
+  print(name, batch, out)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_fused_plan_is_used(name):
+  from surjectors_b200 import _runtime, fused_chains, configs
+
+  c = configs.CONFIGS[name]
+  spec = fused_chains.spec_of(c["make"](), c["dim"], c["dim_x"])
+  assert _runtime.get_plan(spec).is_fused
