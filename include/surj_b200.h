@@ -169,6 +169,11 @@ int64_t surj_made_masks(int32_t n_params, int32_t input_size, const int32_t* hid
 /* Permutation inverse index exactly as permutation.py:31-36 computes it (int32). */
 int surj_permutation_inverse(const int32_t* permutation, int32_t n, int32_t* inverse_out);
 
+/* --- measurement helper (bench.py): a register-only FFMA loop, 16 independent chains per thread,
+ * launched over every SM; *flops_out = floating-point operations one launch executes.  Gives the
+ * measured FP32-pipe peak the small-network kernels are compared against. */
+int surj_bench_fp32_peak(SurjStream stream, int32_t iters, float* sink, double* flops_out);
+
 const char* surj_last_error(void);
 int32_t surj_abi_version(void);
 /* number of fused whole-chain kernels compiled into this library */

@@ -102,6 +102,7 @@ _SIGNATURES = {
                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
   "surj_made_masks": (C.c_int64, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8)]),
   "surj_permutation_inverse": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+  "surj_bench_fp32_peak": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]),
   "surj_last_error": (C.c_char_p, []),
   "surj_abi_version": (C.c_int32, []),
   "surj_registry_size": (C.c_int32, []),

@@ -357,7 +357,9 @@ def trace_chain(transform, d_in, dx, honour_x=True) -> ChainSpec:
   fr = hk.current_frame()
   use_dx = dx if honour_x else 0
   specs, _ = transform._trace(d_in, use_dx)
-  return ChainSpec(specs, d_in, use_dx, fr.layout)
+  spec = ChainSpec(specs, d_in, use_dx, fr.layout)
+  fr.traced.append(spec)
+  return spec
 
 
 class TransformedDistribution:

@@ -506,3 +506,35 @@ extern "C" int surj_adam_step(SurjStream stream, float* params, const float* gra
   if (e != cudaSuccess) return surj_cuda_fail(e, "adam launch");
   return SURJ_OK;
 }
+
+// ------------------------------------------------------------- FP32 peak probe
+__global__ void __launch_bounds__(256) surj_fp32_peak_kernel(float* __restrict__ sink, int iters) {
+  float a[16];
+  const float m = 1.0f + 1e-7f * (float)(threadIdx.x & 3), c = 1e-9f * (float)blockIdx.x;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = (float)(threadIdx.x + k);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = fmaf(a[k], m, c);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += a[k];
+  if (s == 123.456f) sink[0] = s;  // keeps the loop alive without a store on the hot path
+}
+
+extern "C" int surj_bench_fp32_peak(SurjStream stream, int32_t iters, float* sink, double* flops_out) {
+  if (!sink || iters <= 0) {
+    surj_set_error("surj_bench_fp32_peak: bad arguments");
+    return SURJ_E_INVALID;
+  }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = n_sm * 8;
+  surj_fp32_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return surj_cuda_fail(e, "fp32 peak probe launch");
+  if (flops_out) *flops_out = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+  return SURJ_OK;
+}

@@ -195,20 +195,29 @@ struct BlockSink {
   float* tile;   // [(IN+1+OUT) * LDT] staging tile (shared)
   int tid;
 
-  // generic: contraction of A[NA][NT] (rows 0..NA-1) with G[NG][NT]; result (a, g) added to
-  // sg[off(a, g)] through the functor.
+  // generic: contraction of A[NA][NT] (rows 0..NA-1) with G[NG][NT] over the sample index;
+  // result (a, g) is added to sg[off(a, g)].  Work item = a 4x4 tile of (a, g) pairs and one of
+  // KS slices of the sample range; the KS lanes of a tile are adjacent in the warp, combine their
+  // partial sums with shuffles, and lane 0 of the group -- the only thread of the block that ever
+  // touches those addresses -- adds them into sg without atomics (so the result is deterministic).
   template <int NA, int NG, class Off>
   SURJ_DEV void contract(Off off) {
     constexpr int TA = 4, TG = 4;
     constexpr int NTA = (NA + TA - 1) / TA, NTG = (NG + TG - 1) / TG, NE = NTA * NTG;
     constexpr int KS_RAW = NE >= NT ? 1 : NT / NE;
-    constexpr int KS = KS_RAW >= 32 ? 32 : KS_RAW >= 16 ? 16 : KS_RAW >= 8 ? 8 : KS_RAW >= 4 ? 4 : KS_RAW >= 2 ? 2 : 1;
+    constexpr int KS = KS_RAW >= 8 ? 8 : KS_RAW >= 4 ? 4 : KS_RAW >= 2 ? 2 : 1;
     constexpr int KLEN = NT / KS;
+    constexpr int ITEMS = NE * KS;
+    constexpr int ROUNDS = (ITEMS + NT - 1) / NT;
     static_assert(KLEN % 4 == 0, "K slice must be a multiple of 4");
     const float* A = tile;
     const float* G = tile + NA * LDT;
-    for (int w = tid; w < NE * KS; w += NT) {
-      const int e = w % NE, ks = w / NE;
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int w = r * NT + tid;
+      const bool live = w < ITEMS;  // ITEMS is a multiple of KS: a group of KS lanes is live or dead as a whole
+      const int wc = live ? w : 0;
+      const int e = wc / KS, ks = wc % KS;
       const int ta = e % NTA, tg = e / NTA;
       float acc[TA][TG];
 #pragma unroll
@@ -239,15 +248,23 @@ struct BlockSink {
           }
       }
 #pragma unroll
-      for (int a = 0; a < TA; ++a)
+      for (int o = KS / 2; o > 0; o >>= 1)
 #pragma unroll
-        for (int g = 0; g < TG; ++g) {
-          const int ia = ta + a * NTA, ig = tg + g * NTG;
-          if (ia < NA && ig < NG) {
-            const int o = off(ia, ig);
-            if (o >= 0) atomicAdd(sg + o, acc[a][g]);
+        for (int a = 0; a < TA; ++a)
+#pragma unroll
+          for (int g = 0; g < TG; ++g) acc[a][g] += __shfl_xor_sync(0xffffffffu, acc[a][g], o);
+      if (live && ks == 0) {
+#pragma unroll
+        for (int a = 0; a < TA; ++a)
+#pragma unroll
+          for (int g = 0; g < TG; ++g) {
+            const int ia = ta + a * NTA, ig = tg + g * NTG;
+            if (ia < NA && ig < NG) {
+              const int o = off(ia, ig);
+              if (o >= 0) sg[o] += acc[a][g];
+            }
           }
-        }
+      }
     }
   }
 

@@ -7,32 +7,15 @@ their stated shapes; every other chain runs on the generic per-layer kernels.
 
 import torch
 
-from surjectors_b200 import _layers, _sym, configs, hk
+from surjectors_b200 import configs, hk
 
 
 def spec_of(flow, dim, dim_x=0):
   """ChainSpec of `flow` (a function for hk.transform taking method=, y=, x=) without running it."""
-  captured = {}
-
-  def probe(**kw):
-    fr = hk.current_frame()
-    orig = _layers.trace_chain
-
-    def spy(*a, **k):
-      spec = orig(*a, **k)
-      captured["spec"] = spec
-      return spec
-
-    _layers.trace_chain = spy
-    try:
-      return flow(**kw)
-    finally:
-      _layers.trace_chain = orig
-
   y = torch.zeros((1, dim))
   batch = dict(y=y) if dim_x == 0 else dict(y=y, x=torch.zeros((1, dim_x)))
-  hk.transform(probe).init(0, method="log_prob", **batch)
-  return captured["spec"]
+  traced, _ = hk.transform(flow).trace(method="log_prob", **batch)
+  return traced[-1]
 
 
 def fused_chain_specs():

@@ -38,6 +38,7 @@ class _Frame:
     self.counters = {}
     self.module_stack = []
     self.device = None
+    self.traced = []  # ChainSpecs traced in this frame (in call order)
 
 
 def current_frame() -> _Frame:
@@ -215,6 +216,12 @@ class Transformed:
       host[r.offset : r.offset + r.size] = raw[r.module][r.name].reshape(-1)
     flat = torch.from_numpy(host).to(device)
     return tree_from_flat(flat, fr.layout)
+
+  def trace(self, *args, **kwargs):
+    """ChainSpecs of the flows this function evaluates (no arithmetic, no device needed) plus the
+    parameter layout: what `jax.jit` would get out of tracing it."""
+    _, fr = self._run({}, 0, True, args, kwargs)
+    return fr.traced, fr.layout
 
   def apply(self, params, *args, **kwargs):
     if self._apply_rng:

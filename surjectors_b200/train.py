@@ -1,0 +1,120 @@
+"""The training step of the reference's examples as device-side work only:
+`loss, grads = jax.value_and_grad(loss_fn)(params)` with `loss = -sum(lp)` followed by
+`optax.adam(lr)` (examples/coupling_inference_surjection.py:78-90), i.e. fused log_prob+VJP kernel,
+gradient reduction, (data-parallel: one NCCL all-reduce of the flat gradient) and a fused Adam
+update on the flat parameter buffer.  Enqueue-only, CUDA-graph capturable."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from surjectors_b200 import _abi, _runtime, hk
+
+
+class Adam:
+  """optax.adam(lr, b1=0.9, b2=0.999, eps=1e-8) state over one flat buffer (optax 0.2.4 semantics:
+  bias-corrected moments, eps outside the sqrt, eps_root = 0)."""
+
+  def __init__(self, flat: torch.Tensor, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
+    self.lr, self.b1, self.b2, self.eps = float(lr), float(b1), float(b2), float(eps)
+    self.mu = torch.zeros_like(flat)
+    self.nu = torch.zeros_like(flat)
+    self.count = torch.zeros(1, dtype=torch.int32, device=flat.device)
+
+  def update_(self, flat, grads, grad_scale=1.0):
+    st = _abi.lib().surj_adam_step(
+      torch.cuda.current_stream(flat.device).cuda_stream, flat.data_ptr(), grads.data_ptr(), self.mu.data_ptr(),
+      self.nu.data_ptr(), self.count.data_ptr(), flat.numel(), self.lr, self.b1, self.b2, self.eps, float(grad_scale))
+    _abi.check(st, "surj_adam_step")
+
+
+class TrainStep:
+  """One optimisation step on a batch shard.  With a process group the flat gradient (and the
+  loss) are summed over ranks before the update, which is the whole multi-GPU story of this
+  path: samples are independent, parameters are replicated."""
+
+  def __init__(self, model: hk.Transformed, params, example_batch, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8,
+               reduction="sum", process_group=None, method="log_prob"):
+    if not isinstance(getattr(params, "flat", None), torch.Tensor):
+      raise ValueError("params must be the tree returned by model.init (views into one flat buffer)")
+    traced, layout = model.trace(method=method, **{k: v[:1].cpu() for k, v in example_batch.items() if v is not None})
+    if len(traced) != 1:
+      raise ValueError("the model function must evaluate exactly one flow log_prob")
+    if layout.signature() != params.layout.signature():
+      raise ValueError("params do not belong to this model")
+    self.spec = traced[0]
+    self.plan = _runtime.get_plan(self.spec)
+    self.params = params
+    self.flat = params.flat
+    if not self.flat.is_cuda:
+      raise _abi.SurjError("TrainStep needs parameters on a CUDA device (there is no CPU fallback)")
+    self.opt = Adam(self.flat, lr, b1, b2, eps)
+    self.grads = torch.zeros(self.flat.numel() + 4, dtype=torch.float32, device=self.flat.device)
+    self.reduction = reduction
+    self.group = process_group
+    self.world = 1
+    if process_group is not None:
+      import torch.distributed as dist
+
+      self.world = dist.get_world_size(process_group)
+
+  @property
+  def loss(self):
+    """Device scalar: the (global) loss of the last step."""
+    return self.grads[self.flat.numel():self.flat.numel() + 1]
+
+  def launches_per_step(self):
+    return self.plan.launches(backward=True) + 2 + (1 if self.world > 1 else 0)
+
+  def step(self, y, x=None):
+    n = self.flat.numel()
+    B = y.shape[0]
+    g_scale = -1.0 if self.reduction == "sum" else -1.0 / (B * self.world)
+    self.plan.bwd(y, x if self.plan.dim_x > 0 else None, self.flat, g_lp=None, g_scale=g_scale,
+                  g_params=self.grads, loss_out=self.grads[n:n + 1])
+    if self.world > 1:
+      import torch.distributed as dist
+
+      dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
+    self.opt.update_(self.flat, self.grads)
+    return self.loss
+
+  # ---- host-fed steps: the batch lives in (pinned) host memory, the loss is read back
+  def _staging(self, y_host, x_host):
+    if getattr(self, "_stage", None) is None or self._stage[0][0].shape != y_host.shape:
+      dev = self.flat.device
+      self._copy_stream = torch.cuda.Stream(dev)
+      self._stage = []
+      for _ in range(2):
+        ys = torch.empty(y_host.shape, dtype=torch.float32, device=dev)
+        xs = None if x_host is None else torch.empty(x_host.shape, dtype=torch.float32, device=dev)
+        self._stage.append((ys, xs, torch.cuda.Event(), torch.cuda.Event()))
+      self._n_host = 0
+    return self._stage[self._n_host % 2]
+
+  def step_host(self, y_host, x_host=None, loss_out=None):
+    """One step on a host batch: H2D copy on a side stream into one of two staging buffers (so the
+    copy of batch i+1 overlaps the kernels of batch i), the step, and an async D2H copy of the loss
+    into `loss_out` (a pinned host tensor) if given.  Enqueue-only; call `drain()` before reading."""
+    ys, xs, ready, free = self._staging(y_host, x_host)
+    cur = torch.cuda.current_stream(self.flat.device)
+    if self._n_host >= 2:
+      self._copy_stream.wait_event(free)
+    with torch.cuda.stream(self._copy_stream):
+      ys.copy_(y_host, non_blocking=True)
+      if xs is not None:
+        xs.copy_(x_host, non_blocking=True)
+      ready.record(self._copy_stream)
+    cur.wait_event(ready)
+    loss = self.step(ys, xs)
+    free.record(cur)
+    if loss_out is not None:
+      loss_out.copy_(loss, non_blocking=True)
+    self._n_host += 1
+    return loss
+
+  def drain(self):
+    if getattr(self, "_copy_stream", None) is not None:
+      torch.cuda.current_stream(self.flat.device).wait_stream(self._copy_stream)
