@@ -116,7 +116,8 @@ typedef void* SurjStream; /* cudaStream_t */
 enum SurjPlanMode {
   SURJ_MODE_AUTO = 0,  /* fused whole-chain kernel when one is compiled in for this chain, else per-layer */
   SURJ_MODE_FUSED = 1, /* require the fused whole-chain kernel (error if not compiled in) */
-  SURJ_MODE_LAYERED = 2 /* generic per-layer kernels (any width) */
+  SURJ_MODE_LAYERED = 2, /* generic per-layer kernels (any width) */
+  SURJ_MODE_FUSED_GEN1 = 3 /* the build-time generated straight-line kernel for this chain (A/B comparison) */
 };
 
 /* What is added to the summed likelihood contributions of the layers. */
@@ -133,6 +134,7 @@ void surj_plan_destroy(SurjPlan* plan);
 uint64_t surj_plan_key(const SurjPlan* plan);
 int surj_chain_key(const SurjLayerDesc* layers, int32_t n_layers, int32_t dim_in, int32_t dim_x, int64_t n_params,
                    uint64_t* key_out);
+/* 0 = per-layer kernels, 1 = generated straight-line fused kernel, 2 = fused interpreter kernel */
 int32_t surj_plan_is_fused(const SurjPlan* plan);
 int32_t surj_plan_dim_out(const SurjPlan* plan);
 /* number of kernels one fwd / one bwd call launches (for launch accounting) */

@@ -29,7 +29,7 @@ from surjectors_b200._layers import (  # noqa: F401
   Surjector,
   TransformedDistribution,
 )
-from surjectors_b200._runtime import value_and_grad  # noqa: F401
+from surjectors_b200._runtime import execution_mode, value_and_grad  # noqa: F401
 from surjectors_b200._sym import Inverse, RationalQuadraticSpline, ScalarAffine  # noqa: F401
 
 __all__ = [

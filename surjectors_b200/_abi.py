@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(HERE, "_lib")
-LIB_PATH = os.path.join(LIB_DIR, "libsurj_b200.so")
+LIB_PATH = os.environ.get("SURJ_B200_LIB", os.path.join(LIB_DIR, "libsurj_b200.so"))  # override: A/B builds
 KEYLIB_PATH = os.path.join(LIB_DIR, "_surjkey.so")
 
 MAX_NET_LAYERS = 8
@@ -24,7 +24,7 @@ ACT = {
   "identity": 0, "relu": 1, "swish": 2, "tanh": 3, "sigmoid": 4, "softplus": 5, "gelu": 6, "elu": 7,
   "leaky_relu": 8,
 }
-MODE_AUTO, MODE_FUSED, MODE_LAYERED = range(3)
+MODE_AUTO, MODE_FUSED, MODE_LAYERED, MODE_FUSED_GEN1 = range(4)
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = 0, -1, -2, -3, -4
 
 

@@ -147,11 +147,11 @@ def chain_type(spec: ChainSpec) -> str:
   return f"surj::Chain<{spec.dim_in}, {spec.dim_x}, {spec.n_params},\n    {layers}>"
 
 
-def emit_translation_unit(spec: ChainSpec, key: int, name: str, nt: int = 128) -> str:
+def emit_translation_unit(spec: ChainSpec, key: int, name: str, nt: int = 128, min_blocks: int = 1) -> str:
   tag = f"0x{key:016x}"
   return (
     f"// GENERATED by surjectors_b200/_codegen.py for chain '{name}' -- do not edit.\n"
     f'#include "../chain.cuh"\n\n'
     f"using Chain_{tag} = {chain_type(spec)};\n"
-    f"SURJ_REGISTER_CHAIN({tag}, Chain_{tag}, {nt})\n"
+    f"SURJ_REGISTER_CHAIN({tag}, Chain_{tag}, {nt}, {min_blocks})\n"
   )

@@ -20,6 +20,27 @@ BASE_STANDARD_NORMAL, BASE_NONE = 0, 1
 
 _plans = {}
 _plans_lock = threading.Lock()
+_default_mode = _abi.MODE_AUTO
+
+MODES = {"auto": _abi.MODE_AUTO, "fused": _abi.MODE_FUSED, "layered": _abi.MODE_LAYERED, "gen1": _abi.MODE_FUSED_GEN1}
+
+
+class execution_mode:
+  """Context manager selecting which executor new plans use: "auto" (default), "fused" (the
+  in-shared-memory interpreter kernel), "layered" (one kernel per op out of global memory) or "gen1"
+  (the build-time generated kernel of a BASELINE config).  For tests and A/B measurements."""
+
+  def __init__(self, mode):
+    self.mode = MODES[mode] if isinstance(mode, str) else int(mode)
+
+  def __enter__(self):
+    global _default_mode
+    self._prev, _default_mode = _default_mode, self.mode
+    return self
+
+  def __exit__(self, *a):
+    global _default_mode
+    _default_mode = self._prev
 
 
 class Plan:
@@ -38,7 +59,8 @@ class Plan:
     self.spec = spec
     self.base = base
     self.dim_in, self.dim_x, self.dim_out, self.n_params = spec.dim_in, spec.dim_x, spec.dim_out, spec.n_params
-    self.is_fused = bool(lib.surj_plan_is_fused(handle))
+    self.executor = {0: "layered", 1: "gen1", 2: "fused"}[int(lib.surj_plan_is_fused(handle))]
+    self.is_fused = self.executor != "layered"
     self.key = int(lib.surj_plan_key(handle))
     self._ws = {}
 
@@ -121,7 +143,8 @@ def _check_inputs(plan, y, x, flat):
     raise ValueError("flat parameter buffer does not match the plan")
 
 
-def get_plan(spec: ChainSpec, base=BASE_STANDARD_NORMAL, mode=_abi.MODE_AUTO) -> Plan:
+def get_plan(spec: ChainSpec, base=BASE_STANDARD_NORMAL, mode=None) -> Plan:
+  mode = _default_mode if mode is None else mode
   key = (spec.structure(), base, mode)
   with _plans_lock:
     plan = _plans.get(key)

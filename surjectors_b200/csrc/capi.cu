@@ -9,6 +9,7 @@
 #include <string>
 
 #include "plan.h"
+#include "vm_plan.h"
 
 // ------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -290,21 +291,26 @@ extern "C" int surj_plan_create(const SurjLayerDesc* layers, int32_t n_layers, i
   p->mode = mode;
   p->base = base;
   surj_chain_key(p->layers.data(), n_layers, dim_in, dim_x, n_params, &p->key);
-  if (mode != SURJ_MODE_LAYERED) p->fused = surj_find_small(p->key);
-  if (mode == SURJ_MODE_FUSED && !p->fused) {
-    char buf[160];
-    snprintf(buf, sizeof buf, "no fused kernel compiled in for chain key 0x%016llx (%d registered)",
-             (unsigned long long)p->key, surj_registry_count());
+  // Every chain compiles to one program (vm_plan.cu) with two executors.  AUTO picks, in order: a
+  // generated straight-line kernel compiled in for exactly this chain, the fused interpreter kernel
+  // (parameters + a tile of activations fit in shared memory), the per-op executor (any width).
+  std::string why;
+  p->vmp = vm_compile(p, &why);
+  if (mode == SURJ_MODE_AUTO || mode == SURJ_MODE_FUSED_GEN1) p->fused = surj_find_small(p->key);
+  if (p->fused) p->exec = 1;
+  else if (p->vmp && p->vmp->fused_ok && (mode == SURJ_MODE_AUTO || mode == SURJ_MODE_FUSED)) p->exec = 2;
+  else if (p->vmp && (mode == SURJ_MODE_AUTO || mode == SURJ_MODE_LAYERED)) p->exec = 3;
+  if (p->exec == 0) {
+    char buf[400];
+    if (!p->vmp) snprintf(buf, sizeof buf, "chain is not supported: %s", why.c_str());
+    else if (mode == SURJ_MODE_FUSED_GEN1)
+      snprintf(buf, sizeof buf, "no generated kernel compiled in for chain key 0x%016llx (%d registered)",
+               (unsigned long long)p->key, surj_registry_count());
+    else snprintf(buf, sizeof buf, "chain cannot run on the fused kernel: %s", p->vmp->fused_why.c_str());
     surj_set_error(buf);
+    vm_destroy(p->vmp);
     delete p;
     return SURJ_E_UNSUPPORTED;
-  }
-  if (!p->fused) {
-    int r = surj_layered_create(p);
-    if (r) {
-      delete p;
-      return r;
-    }
   }
   *out = p;
   return SURJ_OK;
@@ -312,11 +318,14 @@ extern "C" int surj_plan_create(const SurjLayerDesc* layers, int32_t n_layers, i
 
 extern "C" void surj_plan_destroy(SurjPlan* plan) {
   if (!plan) return;
-  surj_layered_destroy(plan);
+  vm_destroy(plan->vmp);
   delete plan;
 }
 extern "C" uint64_t surj_plan_key(const SurjPlan* plan) { return plan ? plan->key : 0; }
-extern "C" int32_t surj_plan_is_fused(const SurjPlan* plan) { return plan && plan->fused ? 1 : 0; }
+extern "C" int32_t surj_plan_is_fused(const SurjPlan* plan) {
+  if (!plan) return 0;
+  return plan->exec == 3 ? 0 : plan->exec;
+}
 extern "C" int32_t surj_plan_dim_out(const SurjPlan* plan) { return plan ? plan->dim_out : -1; }
 
 static int ensure_device(const SurjPlan* p) {
@@ -326,7 +335,11 @@ static int ensure_device(const SurjPlan* p) {
   if (e != cudaSuccess) return surj_cuda_fail(e, "cudaGetDevice");
   e = cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return surj_cuda_fail(e, "cudaDeviceGetAttribute");
-  if (p->fused) {
+  if (p->exec >= 2) {
+    int r = vm_prepare(p->vmp);
+    if (r) return r;
+  }
+  if (p->exec == 1) {
     e = p->fused->prepare();
     if (e != cudaSuccess) return surj_cuda_fail(e, "cudaFuncSetAttribute(fused chain)");
     e = p->fused->occupancy(&p->fwd_blocks, &p->bwd_blocks);
@@ -341,6 +354,7 @@ static int ensure_device(const SurjPlan* p) {
 }
 
 static int fused_grid(const SurjPlan* p, int64_t B, bool backward) {
+  if (p->exec == 2) return vm_grid(p->vmp, B, backward);
   const int nt = p->fused->nt;
   const int64_t tiles = (B + nt - 1) / nt;
   const int64_t cap = (int64_t)p->n_sm * (backward ? p->bwd_blocks : p->fwd_blocks);
@@ -350,23 +364,24 @@ static int fused_npad(const SurjPlan* p) { return (int)((p->n_params + 1 + 3) / 
 
 extern "C" size_t surj_plan_workspace_bytes(const SurjPlan* plan, int64_t batch, int32_t backward) {
   if (!plan || batch <= 0) return 0;
-  if (plan->fused) {
+  if (plan->exec == 1 || plan->exec == 2) {
     if (!backward) return 0;
     int64_t rows;
     if (ensure_device(plan) == SURJ_OK) rows = fused_grid(plan, batch, true);
+    else if (plan->exec == 2) rows = vm_max_grid(plan->vmp, batch);
     else {  // no device yet: an upper bound of one partial row per possible CTA
       const int64_t tiles = (batch + plan->fused->nt - 1) / plan->fused->nt;
       rows = tiles < 4096 ? tiles : 4096;
     }
     return (size_t)rows * fused_npad(plan) * sizeof(float);
   }
-  return surj_layered_workspace_bytes(plan, batch, backward);
+  return vm_global_workspace_bytes(plan->vmp, batch, backward != 0);
 }
 
 extern "C" int32_t surj_plan_launches(const SurjPlan* plan, int32_t backward) {
   if (!plan) return 0;
-  if (plan->fused) return backward ? 2 : 1;
-  return surj_layered_launches(plan, backward);
+  if (plan->exec == 1 || plan->exec == 2) return backward ? 2 : 1;
+  return vm_global_launches(plan->vmp, 1, backward != 0);
 }
 
 static int check_io(const SurjPlan* plan, const void* y, const void* x, const void* params, int64_t B) {
@@ -391,7 +406,13 @@ extern "C" int surj_chain_logprob_fwd(const SurjPlan* plan, SurjStream stream, c
     return SURJ_E_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan->fused) {
+  if (plan->exec == 2) {
+    r = ensure_device(plan);
+    if (r) return r;
+    return vm_launch(plan->vmp, st, false, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, nullptr, 0.0f, nullptr,
+                     z_out, lp_out, nullptr, nullptr, nullptr, 0, batch, fused_grid(plan, batch, false));
+  }
+  if (plan->exec == 1) {
     r = ensure_device(plan);
     if (r) return r;
     cudaError_t e = plan->fused->fwd(fused_grid(plan, batch, false), st, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params,
@@ -399,7 +420,10 @@ extern "C" int surj_chain_logprob_fwd(const SurjPlan* plan, SurjStream stream, c
     if (e != cudaSuccess) return surj_cuda_fail(e, "chain_fwd_kernel launch");
     return SURJ_OK;
   }
-  return surj_layered_fwd(plan, st, y, x, params, z_out, lp_out, workspace, workspace_bytes, batch);
+  r = ensure_device(plan);
+  if (r) return r;
+  return vm_global_run(plan->vmp, st, false, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, nullptr, 0.0f, nullptr,
+                       z_out, lp_out, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, batch);
 }
 
 // grads[p] = sum_rows partials[row][p]; column np carries sum(lp) -> loss = scale * sum(lp)
@@ -442,7 +466,7 @@ extern "C" int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, c
     return SURJ_E_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan->fused) {
+  if (plan->exec == 1 || plan->exec == 2) {
     r = ensure_device(plan);
     if (r) return r;
     const int grid = fused_grid(plan, batch, true);
@@ -453,10 +477,16 @@ extern "C" int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, c
       return SURJ_E_WORKSPACE;
     }
     float* partials = (float*)workspace;
-    cudaError_t e =
-        plan->fused->bwd(grid, st, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z, partials,
-                         npad, lp_out, nullptr, g_y, g_x, batch);
-    if (e != cudaSuccess) return surj_cuda_fail(e, "chain_bwd_kernel launch");
+    cudaError_t e;
+    if (plan->exec == 2) {
+      r = vm_launch(plan->vmp, st, true, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z,
+                    nullptr, lp_out, g_y, g_x, partials, npad, batch, grid);
+      if (r) return r;
+    } else {
+      e = plan->fused->bwd(grid, st, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z,
+                           partials, npad, lp_out, nullptr, g_y, g_x, batch);
+      if (e != cudaSuccess) return surj_cuda_fail(e, "chain_bwd_kernel launch");
+    }
     const int np = (int)plan->n_params;
     surj_reduce_partials_kernel<<<(np + 1 + 31) / 32, 256, 0, st>>>(partials, grid, npad, np, g_params, loss_out,
                                                                     g_lp ? 1.0f : g_scale);
@@ -464,8 +494,10 @@ extern "C" int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, c
     if (e != cudaSuccess) return surj_cuda_fail(e, "reduce_partials launch");
     return SURJ_OK;
   }
-  return surj_layered_bwd(plan, st, y, x, params, g_lp, g_scale, g_z, g_params, loss_out, lp_out, g_y, g_x, workspace,
-                          workspace_bytes, batch);
+  r = ensure_device(plan);
+  if (r) return r;
+  return vm_global_run(plan->vmp, st, true, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z,
+                       nullptr, lp_out, g_y, g_x, g_params, loss_out, workspace, workspace_bytes, batch);
 }
 
 // -------------------------------------------------------------------------- Adam

@@ -162,8 +162,8 @@ chain_fwd_kernel(int with_base, const float* __restrict__ y, const float* __rest
 // constant g_scale when g_lp == nullptr, e.g. -1 for loss = -sum lp).  Each block accumulates
 // its parameter gradient in shared memory and writes one row of `partials`
 // ([gridDim.x][npad], column NP holds the block's sum of lp).
-template <class CH, int NT>
-__global__ void __launch_bounds__(NT)
+template <class CH, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 chain_bwd_kernel(int with_base, const float* __restrict__ y, const float* __restrict__ x,
                  const float* __restrict__ params, const float* __restrict__ g_lp, float g_scale,
                  const float* __restrict__ g_z, float* __restrict__ partials, int npad,
@@ -222,7 +222,9 @@ chain_bwd_kernel(int with_base, const float* __restrict__ y, const float* __rest
 }
 
 // ------------------------------------------------------------------- registration
-template <class CH, int NT>
+// MINB = CTAs per SM the backward kernel is register-capped for (more resident warps hide the
+// instruction-fetch and shared-memory latency of the straight-line code)
+template <class CH, int NT, int MINB = 1>
 struct SmallLaunch {
   static constexpr int FWD_SMEM = (CH::NP4 + CH::NSCR4) * 4;
   static constexpr int BWD_SMEM = (CH::NP4 + CH::NSCR4 + CH::NP4 + 4 + CH::Ops::MAXW * (NT + 4)) * 4;
@@ -230,12 +232,12 @@ struct SmallLaunch {
   static cudaError_t prepare() {
     cudaError_t e = cudaFuncSetAttribute(chain_fwd_kernel<CH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(chain_bwd_kernel<CH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    return cudaFuncSetAttribute(chain_bwd_kernel<CH, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
   }
   static cudaError_t occupancy(int* fwd_blocks, int* bwd_blocks) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(fwd_blocks, chain_fwd_kernel<CH, NT>, NT, FWD_SMEM);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bwd_blocks, chain_bwd_kernel<CH, NT>, NT, BWD_SMEM);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bwd_blocks, chain_bwd_kernel<CH, NT, MINB>, NT, BWD_SMEM);
   }
   static cudaError_t fwd(int grid, cudaStream_t st, int with_base, const float* y, const float* x,
                          const float* params, float* z, float* lp, long long B) {
@@ -245,7 +247,7 @@ struct SmallLaunch {
   static cudaError_t bwd(int grid, cudaStream_t st, int with_base, const float* y, const float* x,
                          const float* params, const float* g_lp, float g_scale, const float* g_z, float* partials,
                          int npad, float* lp, float* z, float* g_y, float* g_x, long long B) {
-    chain_bwd_kernel<CH, NT><<<grid, NT, BWD_SMEM, st>>>(with_base, y, x, params, g_lp, g_scale, g_z, partials, npad, lp,
+    chain_bwd_kernel<CH, NT, MINB><<<grid, NT, BWD_SMEM, st>>>(with_base, y, x, params, g_lp, g_scale, g_z, partials, npad, lp,
                                                          z, g_y, g_x, B);
     return cudaGetLastError();
   }
@@ -260,9 +262,9 @@ struct SmallLaunch {
 
 }  // namespace surj
 
-#define SURJ_REGISTER_CHAIN(KEY, CHAIN_T, NT)                                                          \
-  namespace {                                                                                          \
-  struct Reg_##KEY {                                                                                   \
-    Reg_##KEY() { surj_register_small(KEY##ull, surj::SmallLaunch<CHAIN_T, NT>::make(), #CHAIN_T); }   \
-  } reg_instance_##KEY;                                                                                \
+#define SURJ_REGISTER_CHAIN(KEY, CHAIN_T, NT, MINB)                                                          \
+  namespace {                                                                                                \
+  struct Reg_##KEY {                                                                                         \
+    Reg_##KEY() { surj_register_small(KEY##ull, surj::SmallLaunch<CHAIN_T, NT, MINB>::make(), #CHAIN_T); }   \
+  } reg_instance_##KEY;                                                                                      \
   }

@@ -17,24 +17,23 @@ struct SurjPlan {
   int32_t mode = 0;
   int32_t base = 0;  // SurjBase
   uint64_t key = 0;
-  const SmallKernels* fused = nullptr;
+  const SmallKernels* fused = nullptr;  // generation-1 fused kernel (per-chain generated code), if registered
+  struct VmPlan* vmp = nullptr;         // generation-2 fused kernel (interpreter), if the chain fits
   // lazily filled device facts
   mutable bool dev_ready = false;
   mutable int n_sm = 148, fwd_blocks = 4, bwd_blocks = 2;
-  // per-layer path (layered.cu)
-  struct Layered* layered = nullptr;
+  int exec = 0;  // 1 generated straight-line kernel, 2 fused interpreter kernel, 3 per-op executor
 };
 
 void surj_set_error(const std::string& msg);
 int surj_cuda_fail(cudaError_t e, const char* what);
 
-// layered.cu
-int surj_layered_create(SurjPlan* plan);
-void surj_layered_destroy(SurjPlan* plan);
-size_t surj_layered_workspace_bytes(const SurjPlan* plan, int64_t batch, int backward);
-int surj_layered_launches(const SurjPlan* plan, int backward);
-int surj_layered_fwd(const SurjPlan* plan, cudaStream_t st, const float* y, const float* x, const float* params,
-                     float* z_out, float* lp_out, void* ws, size_t ws_bytes, int64_t B);
-int surj_layered_bwd(const SurjPlan* plan, cudaStream_t st, const float* y, const float* x, const float* params,
-                     const float* g_lp, float g_scale, const float* g_z, float* g_params, float* loss_out,
-                     float* lp_out, float* g_y, float* g_x, void* ws, size_t ws_bytes, int64_t B);
+// vm_plan.cu -- fused small-network interpreter path
+struct VmPlan* vm_compile(const SurjPlan* plan, std::string* why);
+void vm_destroy(struct VmPlan* v);
+int vm_prepare(struct VmPlan* v);
+int vm_grid(const struct VmPlan* v, int64_t B, bool backward);
+int vm_max_grid(const struct VmPlan* v, int64_t B);
+int vm_launch(struct VmPlan* v, cudaStream_t st, bool backward, int with_base, const float* y, const float* x,
+              const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
+              float* g_y, float* g_x, float* partials, int npad, int64_t B, int grid);

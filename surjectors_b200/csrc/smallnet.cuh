@@ -38,9 +38,9 @@ enum : int { LAYOUT_SPLIT = 0, LAYOUT_INTERLEAVED = 1 };
 #define SURJ_HALF_LOG_2PI 0.91893853320467274178f
 
 // ------------------------------------------------------------------ scalar math
-SURJ_DEV float fast_exp(float x) { return __expf(x); }
-SURJ_DEV float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-SURJ_DEV float softplus_f(float x) { return fmaxf(x, 0.0f) + log1pf(__expf(-fabsf(x))); }
+SURJ_DEV float fast_exp(float x) { return expf(x); }
+SURJ_DEV float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+SURJ_DEV float softplus_f(float x) { return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x))); }
 
 template <int ACT>
 SURJ_DEV float act_fwd(float a) {
@@ -78,7 +78,7 @@ SURJ_DEV float act_bwd(float a, float g) {
     const float t = tanhf(u);
     const float du = c * (1.0f + 3.0f * 0.044715f * a * a);
     return g * (0.5f * (1.0f + t) + 0.5f * a * (1.0f - t * t) * du);
-  } else if constexpr (ACT == ACT_ELU) return a > 0.0f ? g : g * __expf(a);
+  } else if constexpr (ACT == ACT_ELU) return a > 0.0f ? g : g * expf(a);
   else return a > 0.0f ? g : 0.01f * g;
 }
 
@@ -305,7 +305,7 @@ struct BlockSink {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < N; ++i)
-      A[i * LDT + tid] = (y[i] * g_t[i] + __fdividef(g_lc, scr[i])) * fast_sigmoid(sp[DOFF + i]);
+      A[i * LDT + tid] = (y[i] * g_t[i] + g_lc / scr[i]) * fast_sigmoid(sp[DOFF + i]);
     G[tid] = 1.0f;
     __syncthreads();
     contract<N, 1>([](int i, int) -> int { return DOFF + i; });

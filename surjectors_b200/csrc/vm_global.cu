@@ -1,0 +1,328 @@
+// Per-op executor of the chain program for networks too wide for the fused kernel.
+//
+// Same program, same row layout ([row][sample], samples contiguous) as the fused interpreter
+// (vm.cuh), but the rows of a *chunk* of C samples live in the caller's workspace in global memory
+// (mostly L2-resident between kernels for C = 16384) and every matrix product is its own tiled
+// FP32 kernel:
+//   vg_linear  out[j][s] = act(b[j] + sum_i W[i][j] in[i][s])        M = samples, N = outputs, K = inputs
+//   vg_dw      grad[i][j] += sum_s in[i][s] g[j][s]  (+ bias row)      contraction over the samples
+// Runs of per-sample ops between them execute in one vg_elem launch.  Parameters are compacted /
+// masked / transposed once per call by vg_stage into the workspace (the staging table of the plan).
+#include <algorithm>
+#include <cstdio>
+
+#include "plan.h"
+#include "vm_ops.cuh"
+#include "vm_plan.h"
+
+namespace vm {
+
+__global__ void __launch_bounds__(256)
+vg_stage(const int32_t* __restrict__ stage, int n_par, const float* __restrict__ params, float* __restrict__ par,
+         float* __restrict__ grad, int backward, float* __restrict__ scal_g, int n_scal, float* __restrict__ loss_acc) {
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = i0; i < n_par; i += gridDim.x * blockDim.x) {
+    par[i] = stage_value(stage[i], params);
+    if (backward) grad[i] = 0.0f;
+  }
+  if (i0 < n_scal) scal_g[i0] = 0.0f;
+  if (i0 == 0) *loss_acc = 0.0f;
+}
+
+__global__ void vg_scalars(const ScalarJob* __restrict__ jobs, int n_jobs, const float* __restrict__ par,
+                           float* __restrict__ scal) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_jobs) return;
+  const ScalarJob sj = jobs[j];
+  float sum = 0.0f;
+  for (int i = 0; i < sj.n; ++i) sum += logf(par[sj.off + i * sj.stride]);
+  scal[sj.slot] = sum;
+}
+
+// a run of per-sample ops over one chunk; lp / g_lp live in rows ROW_LP / ROW_GLP between launches
+__global__ void __launch_bounds__(128)
+vg_elem(const Op* __restrict__ ops, int n_ops, int first, Io io, float* __restrict__ rows, int C, long long base,
+        long long B, const int32_t* __restrict__ itab, const float* __restrict__ scal, float* __restrict__ scal_g,
+        float* __restrict__ loss_acc) {
+  Ctx<128, 1> c;
+  c.rows = rows; c.T = C; c.col = blockIdx.x * 128 + threadIdx.x; c.base = base; c.B = B;
+  c.itab = itab; c.scal = scal; c.scal_g = scal_g;
+  const long long g = c.sample(0);
+  if (first) {
+    c.lp[0] = 0.0f;
+    c.glp[0] = (io.backward && g < B) ? (io.g_lp != nullptr ? __ldg(io.g_lp + g) : io.g_scale) : 0.0f;
+    c.row(ROW_ONES)[0] = 1.0f;
+    c.row(ROW_GLP)[0] = c.glp[0];
+  } else {
+    c.lp[0] = c.row(ROW_LP)[0];
+    c.glp[0] = c.row(ROW_GLP)[0];
+  }
+  float lp_total = 0.0f;
+  bool stored = false;
+  for (int pc = 0; pc < n_ops; ++pc) {
+    const Op op = ops[pc];
+    exec_simple<128, 1>(c, op, io, lp_total);
+    stored |= op.code == OP_STORE_LP;
+  }
+  c.row(ROW_LP)[0] = c.lp[0];
+  if (stored && io.backward) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lp_total += __shfl_xor_sync(0xffffffffu, lp_total, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss_acc, lp_total);
+  }
+}
+
+// ---- out[j][s] = act(b[j] (+ prev) + sum_i W[i*ld + j] in[i][s]);  CTA tile 128 samples x 64 outputs
+constexpr int LBM = 128, LBN = 64, LBK = 16;
+
+__global__ void __launch_bounds__(256)
+vg_linear(Op op, float* __restrict__ rows, int C, const float* __restrict__ par) {
+  const int in_row = op.a[0], n_in = op.a[1], w_off = op.a[2], ld = op.a[3], out_row = op.a[4], n_out = op.a[5],
+            b_off = op.a[6], act = op.a[7], accumulate = op.a[8], pre_row = op.a[9];
+  __shared__ __align__(16) float As[LBK][LBM];
+  __shared__ __align__(16) float Ws[LBK][LBN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // tx: samples 4tx..4tx+3 and 64+4tx..; ty: outputs 4ty..4ty+3
+  const int s0 = blockIdx.x * LBM, j0 = blockIdx.y * LBN;
+  const float* in = rows + (size_t)in_row * C + s0;
+  const float* w = par + w_off;
+  float acc[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[q][r] = 0.0f;
+
+  // loader coordinates: A tile 16 x 128 floats = 512 float4 (2 per thread), W tile 16 x 64 = 256 float4 (1 per thread)
+  const int a_k0 = tid >> 5, a_c = (tid & 31) * 4;   // rows a_k0 and a_k0 + 8
+  const int w_k = tid >> 4, w_c = (tid & 15) * 4;
+  float4 ra0, ra1, rw;
+  auto fetch = [&](int k0) {
+    const int i0 = k0 + a_k0, i1 = k0 + a_k0 + 8;
+    ra0 = i0 < n_in ? *reinterpret_cast<const float4*>(in + (size_t)i0 * C + a_c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ra1 = i1 < n_in ? *reinterpret_cast<const float4*>(in + (size_t)i1 * C + a_c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int iw = k0 + w_k, jw = j0 + w_c;
+    rw = (iw < n_in && jw < ld) ? *reinterpret_cast<const float4*>(w + (size_t)iw * ld + jw)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < n_in; k0 += LBK) {
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[a_k0][a_c]) = ra0;
+    *reinterpret_cast<float4*>(&As[a_k0 + 8][a_c]) = ra1;
+    *reinterpret_cast<float4*>(&Ws[w_k][w_c]) = rw;
+    __syncthreads();
+    if (k0 + LBK < n_in) fetch(k0 + LBK);
+#pragma unroll
+    for (int k = 0; k < LBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][4 * tx]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + 4 * tx]);
+      const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][4 * ty]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[q][r] = fmaf(wq[q], av[r], acc[q][r]);
+    }
+  }
+  const int acc_row = pre_row >= 0 ? pre_row : out_row;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = j0 + 4 * ty + q;
+    if (j >= n_out) continue;
+    const float b = b_off >= 0 ? par[b_off + j] : 0.0f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const size_t col = (size_t)s0 + 64 * h + 4 * tx;
+      float v[4] = {acc[q][4 * h] + b, acc[q][4 * h + 1] + b, acc[q][4 * h + 2] + b, acc[q][4 * h + 3] + b};
+      if (accumulate) {
+        const float4 p = *reinterpret_cast<const float4*>(rows + (size_t)(acc_row + j) * C + col);
+        v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
+      }
+      if (pre_row >= 0) *reinterpret_cast<float4*>(rows + (size_t)(pre_row + j) * C + col) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(rows + (size_t)(out_row + j) * C + col) =
+          make_float4(act_fwd(act, v[0]), act_fwd(act, v[1]), act_fwd(act, v[2]), act_fwd(act, v[3]));
+    }
+  }
+}
+
+// ---- grad[w_off + i*ld + j] += sum_s in[i][s] g[j][s]; grad[b_off + j] += sum_s g[j][s] (ones row).
+// CTA tile 64 x 64 outputs over a slab of samples; partial sums are added with atomics.
+constexpr int DBI = 64, DBJ = 64, DBK = 32, DLD = DBK + 4;
+
+__global__ void __launch_bounds__(256)
+vg_dw(Op op, const float* __restrict__ rows, int C, int cols, int slab, float* __restrict__ grad) {
+  const int in_row = op.a[0], n_in = op.a[1], g_row = op.a[2], n_out = op.a[3], w_off = op.a[4], ld = op.a[5],
+            b_off = op.a[6];
+  const int NA = n_in + (b_off >= 0 ? 1 : 0), NG = n_out;
+  __shared__ __align__(16) float As[DBI][DLD];
+  __shared__ __align__(16) float Gs[DBJ][DLD];
+  const int tid = threadIdx.x;
+  const int ti = tid & 15, tj = tid >> 4;  // thread owns rows {ti + 16a} x {tj + 16g}
+  const int i0 = blockIdx.x * DBI, j0 = blockIdx.y * DBJ;
+  const int s_begin = blockIdx.z * slab, s_end = min(cols, s_begin + slab);
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) acc[a][g] = 0.0f;
+  const int lr = tid >> 3, lc = (tid & 7) * 4;  // loader: rows lr and lr + 32, 4 samples at lc
+  for (int s0 = s_begin; s0 < s_end; s0 += DBK) {
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lr + 32 * h;
+      const int ia = i0 + r, jg = j0 + r;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vg = va;
+      if (ia < NA && s0 + lc < s_end)
+        va = *reinterpret_cast<const float4*>(rows + (size_t)(ia < n_in ? in_row + ia : (int)ROW_ONES) * C + s0 + lc);
+      if (jg < NG && s0 + lc < s_end) vg = *reinterpret_cast<const float4*>(rows + (size_t)(g_row + jg) * C + s0 + lc);
+      *reinterpret_cast<float4*>(&As[r][lc]) = va;
+      *reinterpret_cast<float4*>(&Gs[r][lc]) = vg;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < DBK; k += 4) {
+      float4 av[4], gv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = *reinterpret_cast<const float4*>(&As[ti + 16 * a][k]);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gv[g] = *reinterpret_cast<const float4*>(&Gs[tj + 16 * g][k]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          acc[a][g] = fmaf(av[a].x, gv[g].x, acc[a][g]);
+          acc[a][g] = fmaf(av[a].y, gv[g].y, acc[a][g]);
+          acc[a][g] = fmaf(av[a].z, gv[g].z, acc[a][g]);
+          acc[a][g] = fmaf(av[a].w, gv[g].w, acc[a][g]);
+        }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int ia = i0 + ti + 16 * a, jg = j0 + tj + 16 * g;
+      if (ia < NA && jg < NG) atomicAdd(grad + (ia < n_in ? w_off + ia * ld + jg : b_off + jg), acc[a][g]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+vg_writeback(const int32_t* __restrict__ grad_dst, const int32_t* __restrict__ grad_aux, int n_prim,
+             const float* __restrict__ grad, const float* __restrict__ par, const float* __restrict__ scal_g,
+             const float* __restrict__ params, float* __restrict__ g_params, const float* __restrict__ loss_acc,
+             float* __restrict__ loss_out, float loss_scale) {
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = i0; i < n_prim; i += gridDim.x * blockDim.x)
+    writeback_grad(grad_dst[i], grad_aux[i], grad[i], par[i], scal_g, params, g_params);
+  if (i0 == 0 && loss_out != nullptr) *loss_out = loss_scale * *loss_acc;
+}
+
+}  // namespace vm
+
+// ------------------------------------------------------------------------------ host
+namespace {
+inline size_t a256(size_t n) { return (n + 255) & ~(size_t)255; }
+inline int chunk_cols(int64_t B, int n_rows) {
+  // rows of one chunk must stay within ~1.5 GB and, when possible, L2-friendly (16384 samples)
+  int64_t c = std::min<int64_t>(16384, (B + 127) / 128 * 128);
+  const int64_t cap = ((int64_t)1536 << 20) / ((int64_t)n_rows * 4) / 128 * 128;
+  c = std::max<int64_t>(128, std::min(c, cap));
+  return (int)c;
+}
+struct Carve {
+  float *par, *grad, *scal, *scal_g, *loss, *rows;
+  size_t total;
+};
+Carve carve(const VmPlan* v, void* ws, int C, bool backward) {
+  Carve k;
+  size_t o = 0;
+  auto take = [&](size_t floats) { float* p = ws ? (float*)((char*)ws + o) : nullptr; o += a256(floats * 4); return p; };
+  k.par = take(v->stage.size());
+  k.grad = take(backward ? v->stage.size() : 1);
+  k.scal = take(std::max(v->n_scalars, 1));
+  k.scal_g = take(std::max(v->n_scalars, 1));
+  k.loss = take(1);
+  k.rows = take((size_t)v->n_rows * C);
+  k.total = o;
+  return k;
+}
+}  // namespace
+
+size_t vm_global_workspace_bytes(const VmPlan* v, int64_t B, bool backward) {
+  return carve(v, nullptr, chunk_cols(B, v->n_rows), backward).total;
+}
+
+int vm_global_launches(const VmPlan* v, int64_t B, bool backward) {
+  const std::vector<vm::Op>& ops = backward ? v->ops_bwd : v->ops_fwd;
+  int per_chunk = 0;
+  bool in_run = false;
+  for (const vm::Op& op : ops) {
+    const bool mat = op.code == vm::OP_LINEAR || op.code == vm::OP_LINEAR_DW;
+    if (mat) { ++per_chunk; in_run = false; }
+    else if (!in_run) { ++per_chunk; in_run = true; }
+  }
+  const int C = chunk_cols(B, v->n_rows);
+  const int chunks = (int)((B + C - 1) / C);
+  return 2 + per_chunk * chunks + (backward ? 1 : 0);
+}
+
+int vm_global_run(VmPlan* v, cudaStream_t st, bool backward, int with_base, const float* y, const float* x,
+                  const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
+                  float* g_y, float* g_x, float* g_params, float* loss_out, void* ws, size_t ws_bytes, int64_t B) {
+  const int C = chunk_cols(B, v->n_rows);
+  Carve k = carve(v, ws, C, backward);
+  if (!ws || ws_bytes < k.total || ((uintptr_t)ws & 255u)) {
+    surj_set_error("workspace too small or not 256-byte aligned for the per-layer path");
+    return SURJ_E_WORKSPACE;
+  }
+  const vm::Program& P = v->prog;
+  const std::vector<vm::Op>& ops = backward ? v->ops_bwd : v->ops_fwd;
+  const vm::Op* d_ops = backward ? v->d_ops_bwd : v->d_ops_fwd;
+  const int n_par = (int)v->stage.size();
+  vm::Io io;
+  io.y = y; io.x = x; io.g_lp = g_lp; io.g_z = g_z; io.z_out = z_out; io.lp_out = lp_out; io.g_y = g_y; io.g_x = g_x;
+  io.g_scale = g_scale; io.with_base = with_base; io.backward = backward ? 1 : 0;
+
+  vm::vg_stage<<<std::min((n_par + 255) / 256, 148 * 8), 256, 0, st>>>(P.stage, n_par, params, k.par, k.grad, backward ? 1 : 0,
+                                                                      k.scal_g, v->n_scalars, k.loss);
+  if (!v->sjobs.empty())
+    vm::vg_scalars<<<((int)v->sjobs.size() + 31) / 32, 32, 0, st>>>(P.sjobs, (int)v->sjobs.size(), k.par, k.scal);
+  for (int64_t base = 0; base < B; base += C) {
+    const int cols = (int)std::min<int64_t>(C, (B - base + 127) / 128 * 128);  // columns in use (multiple of 128)
+    size_t pc = 0;
+    bool first = true;
+    while (pc < ops.size()) {
+      const vm::Op& op = ops[pc];
+      if (op.code == vm::OP_LINEAR) {
+        dim3 grid(cols / vm::LBM, (op.a[5] + vm::LBN - 1) / vm::LBN);
+        vm::vg_linear<<<grid, 256, 0, st>>>(op, k.rows, C, k.par);
+        ++pc;
+      } else if (op.code == vm::OP_LINEAR_DW) {
+        const int NA = op.a[1] + (op.a[6] >= 0 ? 1 : 0), NG = op.a[3];
+        const int slab = 2048;
+        dim3 grid((NA + vm::DBI - 1) / vm::DBI, (NG + vm::DBJ - 1) / vm::DBJ, (cols + slab - 1) / slab);
+        vm::vg_dw<<<grid, 256, 0, st>>>(op, k.rows, C, cols, slab, k.grad);
+        ++pc;
+      } else {
+        size_t e = pc;
+        while (e < ops.size() && ops[e].code != vm::OP_LINEAR && ops[e].code != vm::OP_LINEAR_DW) ++e;
+        vm::vg_elem<<<cols / 128, 128, 0, st>>>(d_ops + pc, (int)(e - pc), first ? 1 : 0, io, k.rows, C, base, B, P.itab,
+                                              k.scal, k.scal_g, k.loss);
+        first = false;
+        pc = e;
+      }
+    }
+  }
+  if (backward) {
+    cudaError_t e = cudaMemsetAsync(g_params, 0, (size_t)v->n_params * 4, st);
+    if (e != cudaSuccess) return surj_cuda_fail(e, "cudaMemsetAsync(g_params)");
+    vm::vg_writeback<<<std::min((n_par + 255) / 256, 148 * 8), 256, 0, st>>>(
+        P.grad_dst, P.grad_aux, n_par, k.grad, k.par, k.scal_g, params, g_params, k.loss, loss_out,
+        g_lp ? 1.0f : g_scale);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return surj_cuda_fail(e, "per-layer path launch");
+  return SURJ_OK;
+}

@@ -1,0 +1,311 @@
+// Per-sample ("simple") ops of the chain program: everything except the matrix products.
+// A thread owns S sample columns of the row workspace and touches nothing else, so these ops
+// need no synchronisation.  Shared by the fused in-shared-memory interpreter (vm_kernels.cuh) and
+// the per-op global-memory executor (vm_global.cu).
+#pragma once
+#include "vm.cuh"
+#include "vm_rqs.cuh"
+
+namespace vm {
+
+enum : int { ROW_ONES = 0, ROW_LP = 1, ROW_GLP = 2, ROW_FIRST_FREE = 3 };
+
+struct Io {  // caller buffers of one C-ABI call
+  const float* y; const float* x; const float* g_lp; const float* g_z;
+  float* z_out; float* lp_out; float* g_y; float* g_x;
+  float g_scale; int with_base; int backward;
+};
+
+template <int NT, int S>
+struct Ctx {
+  float* rows;          // [n_rows][T]
+  int T;                // row stride in floats
+  int col;              // first column of this thread
+  long long base;       // global sample index of column 0
+  long long B;          // batch size
+  const int32_t* itab;
+  const float* scal;    // [n_scalars] per-plan scalars (LULinear log-dets)
+  float* scal_g;        // [n_scalars] accumulated cotangents of those scalars
+  float lp[S];
+  float glp[S];
+  VM_DEV float* row(int r) const { return rows + (size_t)r * T + col; }
+  VM_DEV long long sample(int s) const { return base + col + s * NT; }
+};
+
+template <int NT, int S>
+struct ThRow {  // theta accessor: rows th0 + k, this thread's column
+  float* p;
+  int T;
+  VM_DEV float& operator()(int k) const { return p[(size_t)k * T]; }
+};
+
+template <int NT, int S>
+VM_DEV void op_load(Ctx<NT, S>& c, const Op& op, const float* __restrict__ src) {
+  const int dst = op.a[0], n = op.a[1];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const long long g = c.sample(s);
+    float* r = c.row(dst) + s * NT;
+    if (g < c.B) {
+      const float* p = src + g * n;
+      if ((n & 3) == 0) {
+        for (int d = 0; d < n; d += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p + d));
+          r[(size_t)d * c.T] = t.x;
+          r[(size_t)(d + 1) * c.T] = t.y;
+          r[(size_t)(d + 2) * c.T] = t.z;
+          r[(size_t)(d + 3) * c.T] = t.w;
+        }
+      } else {
+        for (int d = 0; d < n; ++d) r[(size_t)d * c.T] = __ldg(p + d);
+      }
+    } else {
+      for (int d = 0; d < n; ++d) r[(size_t)d * c.T] = 0.0f;
+    }
+  }
+}
+
+template <int NT, int S>
+VM_DEV void op_store(Ctx<NT, S>& c, const Op& op, float* __restrict__ dst) {
+  if (dst == nullptr) return;
+  const int src = op.a[0], n = op.a[1];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const long long g = c.sample(s);
+    if (g >= c.B) continue;
+    const float* r = c.row(src) + s * NT;
+    float* p = dst + g * n;
+    if ((n & 3) == 0) {
+      for (int d = 0; d < n; d += 4)
+        *reinterpret_cast<float4*>(p + d) = make_float4(r[(size_t)d * c.T], r[(size_t)(d + 1) * c.T],
+                                                        r[(size_t)(d + 2) * c.T], r[(size_t)(d + 3) * c.T]);
+    } else {
+      for (int d = 0; d < n; ++d) p[d] = r[(size_t)d * c.T];
+    }
+  }
+}
+
+template <int NT, int S>
+VM_DEV void op_affine(Ctx<NT, S>& c, const Op& op) {
+  const int in_row = op.a[0], out_row = op.a[1], n_t = op.a[2], it = op.a[3], sh = op.a[4], ss = op.a[5], ls = op.a[6],
+            lss = op.a[7], inner = op.a[8];
+  for (int k = 0; k < n_t; ++k) {
+    const int d = c.itab[it + k];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const float y = c.row(in_row + d)[s * NT], m = c.row(sh + k * ss)[s * NT], l = c.row(ls + k * lss)[s * NT];
+      float z;
+      if (inner == INNER_AFFINE) {  // ScalarAffine(m, exp(l)).inverse: z = (y - m) e^{-l}, ld = -l
+        z = (y - m) * expf(-l);
+        c.lp[s] -= l;
+      } else {  // Inverse(ScalarAffine).inverse = forward: z = e^{l} y + m, ld = +l
+        z = fmaf(expf(l), y, m);
+        c.lp[s] += l;
+      }
+      c.row(out_row + d)[s * NT] = z;
+    }
+  }
+}
+
+// cotangents; thetas are overwritten by their cotangents
+template <int NT, int S>
+VM_DEV void op_affine_bwd(Ctx<NT, S>& c, const Op& op) {
+  const int in_row = op.a[0], n_t = op.a[1], it = op.a[2], sh = op.a[3], ss = op.a[4], ls = op.a[5], lss = op.a[6],
+            inner = op.a[7], gout = op.a[8], gin = op.a[9];
+  for (int k = 0; k < n_t; ++k) {
+    const int d = c.itab[it + k];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const float y = c.row(in_row + d)[s * NT];
+      float* pm = c.row(sh + k * ss) + s * NT;
+      float* pl = c.row(ls + k * lss) + s * NT;
+      const float m = *pm, l = *pl, gz = c.row(gout + d)[s * NT], glc = c.glp[s];
+      float gy, gm, gs;
+      if (inner == INNER_AFFINE) {
+        const float e = expf(-l);
+        const float z = (y - m) * e;
+        gy = gz * e;
+        gm = -gy;
+        gs = -gz * z - glc;
+      } else {
+        const float e = expf(l);
+        gy = gz * e;
+        gm = gz;
+        gs = gz * e * y + glc;
+      }
+      *pm = gm;
+      *pl = gs;
+      c.row(gin + d)[s * NT] = gy;
+    }
+  }
+}
+
+template <int NT, int S>
+VM_DEV void op_rqs(Ctx<NT, S>& c, const Op& op) {
+  const int in_row = op.a[0], out_row = op.a[1], n_t = op.a[2], it = op.a[3], th = op.a[4], K = op.a[5];
+  const bool forward = op.a[6] == INNER_RQS_INV;
+  const int P = 3 * K + 1;
+  for (int k = 0; k < n_t; ++k) {
+    const int d = c.itab[it + k];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const float v = c.row(in_row + d)[s * NT];
+      ThRow<NT, S> acc{c.row(th + k * P) + s * NT, c.T};
+      RqsBin b;
+      rqs_locate(acc, K, op.f0, op.f1, v, forward, b);
+      float out, ld;
+      rqs_eval(b, K, op.f0, op.f1, v, forward, out, ld);
+      c.row(out_row + d)[s * NT] = out;
+      c.lp[s] += ld;
+    }
+  }
+}
+
+template <int NT, int S>
+VM_DEV void op_rqs_bwd(Ctx<NT, S>& c, const Op& op) {
+  const int in_row = op.a[0], n_t = op.a[1], it = op.a[2], th = op.a[3], K = op.a[4];
+  const bool forward = op.a[5] == INNER_RQS_INV;
+  const int gout = op.a[6], gin = op.a[7];
+  const int P = 3 * K + 1;
+  for (int k = 0; k < n_t; ++k) {
+    const int d = c.itab[it + k];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const float v = c.row(in_row + d)[s * NT];
+      ThRow<NT, S> acc{c.row(th + k * P) + s * NT, c.T};
+      c.row(gin + d)[s * NT] = rqs_bwd(acc, K, op.f0, op.f1, v, forward, c.row(gout + d)[s * NT], c.glp[s]);
+    }
+  }
+}
+
+template <int NT, int S>
+VM_DEV void op_normal_lp(Ctx<NT, S>& c, const Op& op) {
+  const int v = op.a[0], n = op.a[1], mu = op.a[2], ls = op.a[3];
+  for (int j = 0; j < n; ++j) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const float l = c.row(ls + j)[s * NT];
+      const float r = (c.row(v + j)[s * NT] - c.row(mu + j)[s * NT]) * expf(-l);
+      c.lp[s] += -0.5f * r * r - l - VM_HALF_LOG_2PI;
+    }
+  }
+}
+
+template <int NT, int S>
+VM_DEV void op_normal_lp_bwd(Ctx<NT, S>& c, const Op& op) {
+  const int v = op.a[0], n = op.a[1], mu = op.a[2], ls = op.a[3], gv = op.a[4];
+  for (int j = 0; j < n; ++j) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      float* pm = c.row(mu + j) + s * NT;
+      float* pl = c.row(ls + j) + s * NT;
+      const float e = expf(-*pl);
+      const float r = (c.row(v + j)[s * NT] - *pm) * e;
+      const float g = c.glp[s];
+      *pm = g * r * e;
+      *pl = g * (r * r - 1.0f);
+      c.row(gv + j)[s * NT] = -g * r * e;
+    }
+  }
+}
+
+// Executes one simple op; returns false if `op` is a matrix op the caller must handle.
+// lp_total accumulates the log-probs of valid samples stored by OP_STORE_LP (for the loss).
+template <int NT, int S>
+VM_DEV bool exec_simple(Ctx<NT, S>& c, const Op& op, const Io& io, float& lp_total) {
+  switch (op.code) {
+    case OP_LOAD: op_load<NT, S>(c, op, op.a[2] == 0 ? io.y : io.x); return true;
+    case OP_STORE: op_store<NT, S>(c, op, op.a[2] == 0 ? io.z_out : (op.a[2] == 1 ? io.g_y : io.g_x)); return true;
+    case OP_GATHER:
+      for (int k = 0; k < op.a[1]; ++k) {
+        const float* src = c.row(c.itab[op.a[2] + k]);
+        float* dst = c.row(op.a[0] + k);
+#pragma unroll
+        for (int s = 0; s < S; ++s) dst[s * NT] = src[s * NT];
+      }
+      return true;
+    case OP_SCATTER_ADD:
+      for (int k = 0; k < op.a[1]; ++k) {
+        const float* src = c.row(op.a[0] + k);
+        float* dst = c.row(c.itab[op.a[2] + k]);
+#pragma unroll
+        for (int s = 0; s < S; ++s) dst[s * NT] += src[s * NT];
+      }
+      return true;
+    case OP_COPY:
+      for (int k = 0; k < op.a[2]; ++k)
+#pragma unroll
+        for (int s = 0; s < S; ++s) c.row(op.a[0] + k)[s * NT] = c.row(op.a[1] + k)[s * NT];
+      return true;
+    case OP_ADD:
+      for (int k = 0; k < op.a[2]; ++k)
+#pragma unroll
+        for (int s = 0; s < S; ++s) c.row(op.a[0] + k)[s * NT] += c.row(op.a[1] + k)[s * NT];
+      return true;
+    case OP_ZERO:
+      for (int k = 0; k < op.a[1]; ++k)
+#pragma unroll
+        for (int s = 0; s < S; ++s) c.row(op.a[0] + k)[s * NT] = 0.0f;
+      return true;
+    case OP_AFFINE: op_affine<NT, S>(c, op); return true;
+    case OP_RQS: op_rqs<NT, S>(c, op); return true;
+    case OP_NORMAL_LP: op_normal_lp<NT, S>(c, op); return true;
+    case OP_ADD_SCALAR:
+#pragma unroll
+      for (int s = 0; s < S; ++s) c.lp[s] += c.scal[op.a[0]];
+      return true;
+    case OP_BASE:
+      if (io.with_base) {
+        for (int k = 0; k < op.a[1]; ++k)
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const float z = c.row(op.a[0] + k)[s * NT];
+            c.lp[s] += -0.5f * z * z - VM_HALF_LOG_2PI;
+          }
+      }
+      return true;
+    case OP_STORE_LP:
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const long long g = c.sample(s);
+        if (g < c.B) {
+          if (io.lp_out != nullptr) io.lp_out[g] = c.lp[s];
+          lp_total += c.lp[s];
+        }
+      }
+      return true;
+    case OP_BASE_BWD:
+      for (int k = 0; k < op.a[1]; ++k)
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const long long g = c.sample(s);
+          float v = io.with_base ? -c.glp[s] * c.row(op.a[0] + k)[s * NT] : 0.0f;
+          if (io.g_z != nullptr && g < c.B) v += __ldg(io.g_z + g * op.a[1] + k);
+          c.row(op.a[2] + k)[s * NT] = v;
+        }
+      return true;
+    case OP_NORMAL_LP_BWD: op_normal_lp_bwd<NT, S>(c, op); return true;
+    case OP_AFFINE_BWD: op_affine_bwd<NT, S>(c, op); return true;
+    case OP_RQS_BWD: op_rqs_bwd<NT, S>(c, op); return true;
+    case OP_ACT_BWD:
+      for (int k = 0; k < op.a[2]; ++k)
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          float* g = c.row(op.a[0] + k) + s * NT;
+          *g = act_bwd(op.a[3], c.row(op.a[1] + k)[s * NT], *g);
+        }
+      return true;
+    case OP_SCALAR_BWD: {
+      float v = 0.0f;
+#pragma unroll
+      for (int s = 0; s < S; ++s) v += c.glp[s];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(c.scal_g + op.a[0], v);
+      return true;
+    }
+    default: return false;
+  }
+}
+
+}  // namespace vm

@@ -5,6 +5,8 @@ resulting ChainSpec to the code generator.  The BASELINE.json small-network conf
 their stated shapes; every other chain runs on the generic per-layer kernels.
 """
 
+import os
+
 import torch
 
 from surjectors_b200 import configs, hk
@@ -22,5 +24,7 @@ def fused_chain_specs():
   out = []
   for name in ("cfg1", "cfg2", "cfg3"):
     c = configs.CONFIGS[name]
-    out.append((name, spec_of(c["make"](), c["dim"], c["dim_x"]), 128))
+    nt = int(os.environ.get("SURJ_GEN1_NT", "64"))
+    minb = int(os.environ.get("SURJ_GEN1_MINB", "8"))
+    out.append((name, spec_of(c["make"](), c["dim"], c["dim_x"]), nt, minb))
   return out

@@ -16,7 +16,7 @@ from oracle import configs as ocfg
 from oracle import hk as ohk
 from surjectors_b200 import configs as pcfg
 from surjectors_b200 import hk as phk
-from surjectors_b200 import value_and_grad
+from surjectors_b200 import execution_mode, value_and_grad
 
 LP_RTOL = 1e-5
 GRAD_RTOL = 1e-4
@@ -83,7 +83,12 @@ def grad_errors(grads, ref):
   return out
 
 
-def check_config(name, batch=256, device="cuda:0", check_grad=True, seed=0, w_std=0.3, **scale):
+def check_config(name, batch=256, device="cuda:0", check_grad=True, seed=0, w_std=0.3, mode="auto", **scale):
+  with execution_mode(mode):
+    return _check_config(name, batch, device, check_grad, seed, w_std, **scale)
+
+
+def _check_config(name, batch, device, check_grad, seed, w_std, **scale):
   pm, pparams, om, oparams, y64, x64 = build_pair(name, batch, seed, w_std, **scale)
   dev = torch.device(device)
   params = to_device(pparams, dev)

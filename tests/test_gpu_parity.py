@@ -22,4 +22,20 @@ def test_fused_plan_is_used(name):
 
   c = configs.CONFIGS[name]
   spec = fused_chains.spec_of(c["make"](), c["dim"], c["dim_x"])
-  assert _runtime.get_plan(spec).is_fused
+  assert _runtime.get_plan(spec).executor == "gen1"
+
+
+@pytest.mark.parametrize("mode", ["fused", "layered"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_small_configs_both_executors(name, mode):
+  out = parity.check_config(name, batch=300, check_grad=True, mode=mode)
+  print(name, mode, out)
+
+
+@pytest.mark.parametrize("mode", ["fused", "layered"])
+@pytest.mark.parametrize("name", ["cfg4", "cfg5"])
+def test_scaled_wide_configs(name, mode):
+  """cfg4 (spline couplings + spline funnel) and cfg5 (conditional MAF + LULinear + Permutation)
+  at oracle-sized shapes, through both executors."""
+  out = parity.check_config(name, batch=200, check_grad=True, mode=mode, **parity.SMALL[name])
+  print(name, mode, out)
