@@ -157,9 +157,10 @@ def randomize(params, seed, w_std=0.3, b_val=None, b_std=0.1):
       elif name == "b":
         new = rng.standard_normal(val.shape) * b_std if b_val is None else np.full(val.shape, b_val)
       elif name in ("lower_entries", "upper_entries"):
-        new = rng.standard_normal(val.shape) * (0.3 / np.sqrt(max(val.shape[0], 1)) ** 0.5)
+        n_dim = max(1.0, (1.0 + np.sqrt(1.0 + 8.0 * val.shape[0])) / 2.0)  # entries = n (n - 1) / 2
+        new = rng.standard_normal(val.shape) * (0.5 / n_dim)
       elif name == "diag_entries":
-        new = 1.0 + 0.3 * rng.standard_normal(val.shape)
+        new = 0.5413 + 0.2 * rng.standard_normal(val.shape)  # softplus(0.5413) = 1: keeps deep chains conditioned
       else:
         new = val.numpy()
       out[mod][name] = torch.as_tensor(np.asarray(new), dtype=val.dtype).reshape(val.shape).clone()

@@ -622,7 +622,15 @@ int vm_prepare(VmPlan* v) {
     return SURJ_OK;
   }
   VmKernel k = vm_kernel_for(v->nt, v->s);
-  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(v->smem_fwd, v->smem_bwd));
+  // the attribute is per kernel, not per plan: always raise it to the device limit so plans with
+  // different footprints can share the kernel
+  int optin = 227 * 1024;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if ((size_t)optin < std::max(v->smem_fwd, v->smem_bwd)) {
+    surj_set_error("fused kernel needs more shared memory than this device offers");
+    return SURJ_E_CUDA;
+  }
+  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   if (e != cudaSuccess) return surj_cuda_fail(e, "cudaFuncSetAttribute(vm_kernel)");
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v->occ_fwd, k, v->nt, v->smem_fwd);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v->occ_bwd, k, v->nt, v->smem_bwd);

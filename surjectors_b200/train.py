@@ -10,7 +10,7 @@ import ctypes as C
 
 import torch
 
-from surjectors_b200 import _abi, _runtime, hk
+from surjectors_b200 import _abi, _runtime, hk, parallel
 
 
 class Adam:
@@ -75,9 +75,7 @@ class TrainStep:
     self.plan.bwd(y, x if self.plan.dim_x > 0 else None, self.flat, g_lp=None, g_scale=g_scale,
                   g_params=self.grads, loss_out=self.grads[n:n + 1])
     if self.world > 1:
-      import torch.distributed as dist
-
-      dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
+      parallel.allreduce_flat_(self.grads, self.group)  # the one collective of the path: flat gradient + loss
     self.opt.update_(self.flat, self.grads)
     return self.loss
 

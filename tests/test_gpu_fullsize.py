@@ -1,0 +1,50 @@
+"""BASELINE.json's two wide configs at their FULL widths (cfg4: 8 spline couplings + spline funnel,
+64 bins, hidden 256, 64 -> 16; cfg5: conditional 16-layer MAF + LULinear + Permutation, dim 128,
+hidden 512): oracle parity on a batch the oracle finishes in seconds, and size-independent
+properties at a large batch (chunk invariance of log-probs, additivity of gradients over batch
+shards -- the property data-parallel training relies on)."""
+
+import numpy as np
+import pytest
+import torch
+
+from tests import parity
+from surjectors_b200 import value_and_grad
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["cfg4", "cfg5"])
+def test_full_width_parity(name):
+  out = parity.check_config(name, batch=192, check_grad=True, w_std=0.15)
+  print(name, out)
+
+
+@pytest.mark.parametrize("name,batch", [("cfg4", 1 << 17), ("cfg5", 1 << 17)])
+def test_large_batch_properties(name, batch):
+  pm, pparams, om, oparams, y64, x64 = parity.build_pair(name, 8, 0, 0.15)
+  dev = torch.device("cuda:0")
+  params = parity.to_device(pparams, dev)
+  c = parity.pcfg.CONFIGS[name]
+  g = torch.Generator(device="cpu").manual_seed(7)
+  y = torch.randn((batch, c["dim"]), generator=g).to(dev)
+  x = torch.randn((batch, c["dim_x"]), generator=g).to(dev) if c["dim_x"] else None
+  kw = lambda sl: dict(y=y[sl]) if x is None else dict(y=y[sl], x=x[sl])  # noqa: E731
+  lp = pm.apply(params, None, method="log_prob", **kw(slice(None)))
+  assert lp.shape == (batch,) and bool(torch.isfinite(lp).all())
+  # chunk invariance: a sample's log-prob does not depend on the batch it sits in
+  for sl in (slice(0, 100), slice(batch // 2 - 33, batch // 2 + 31), slice(batch - 77, batch)):
+    lp_small = pm.apply(params, None, method="log_prob", **kw(sl))
+    assert torch.equal(lp_small, lp[sl]), float((lp_small - lp[sl]).abs().max())
+  # gradients add over batch shards
+  def loss(p, sl):
+    return -torch.sum(pm.apply(p, None, method="log_prob", **kw(sl)))
+
+  half = batch // 2
+  l_all, g_all = value_and_grad(lambda p: loss(p, slice(None)))(params)
+  l_a, g_a = value_and_grad(lambda p: loss(p, slice(0, half)))(params)
+  l_b, g_b = value_and_grad(lambda p: loss(p, slice(half, batch)))(params)
+  assert abs(float(l_all) - float(l_a) - float(l_b)) <= 1e-5 * abs(float(l_all))
+  num = (g_all.flat - g_a.flat - g_b.flat).abs().max()
+  den = g_all.flat.abs().max()
+  assert float(num) <= 1e-4 * float(den), (float(num), float(den))
