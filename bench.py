@@ -161,6 +161,11 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------- our arm
+def _dbg(msg):
+  if os.environ.get("SURJ_BENCH_DEBUG"):
+    print(f"[bench r{os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_b200(args):
   import numpy as np
   import torch
@@ -208,6 +213,7 @@ def run_b200(args):
     k = i % P
     return ts.step(dev_y[k], dev_x[k] if DX else None)
 
+  _dbg("model + data ready")
   # --- CUDA graphs: one graph = one pass over the pool (P consecutive steps); singles for the remainder
   use_graph = not args.no_graph
   full = singles = None
@@ -217,6 +223,7 @@ def run_b200(args):
     for i in range(3):  # allocate workspaces, load kernels, NCCL warm-up outside capture
       step(i)
   torch.cuda.synchronize(dev)
+  _dbg("eager warm-up done")
   if use_graph:
     try:
       with torch.cuda.stream(stream):
@@ -262,6 +269,7 @@ def run_b200(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
+  _dbg(f"graphs captured: {use_graph}")
   # --- timed region: resident inputs
   with torch.cuda.stream(stream):
     run_steps(args.warmup)
@@ -277,12 +285,15 @@ def run_b200(args):
       # keep the sampler alive for at least a few samples when the region is very short
       ms = e0.elapsed_time(e1)
       if ms < 400.0:
-        t_end = time.perf_counter() + 0.4
-        while time.perf_counter() < t_end:
+        # same load, outside the timed region, until nvidia-smi has a few samples; the number of extra
+        # passes is agreed between ranks (every step contains a collective)
+        extra = int(max_over_ranks(400.0 / max(ms / args.steps, 1e-3) / P)) + 1
+        for _ in range(min(extra, 4096)):
           run_steps(P)
         torch.cuda.synchronize(dev)
     barrier()
     torch.cuda.synchronize(dev)
+  _dbg("timed region done")
   ms = max_over_ranks(ms)
   value = world * B * args.steps / (ms * 1e-3)
   loss_resident = float(ts.loss.item())
@@ -331,6 +342,7 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     fp32_peak = 5 * fl.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
 
+  _dbg("roofline done")
   need, dense = _cost.forward_flops(ts.spec)
   flops_launch = 3.0 * need * B
   bytes_launch = float(_cost.forward_bytes(ts.spec) * B + 4 * n_par)
@@ -370,6 +382,7 @@ def run_b200(args):
     h1.record(stream)
     torch.cuda.synchronize(dev)
     barrier()
+  _dbg("e2e done")
   e2e_ms = max_over_ranks(h0.elapsed_time(h1))
   e2e = {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
          "h2d_bytes_per_step": 4 * B * (D + DX), "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
@@ -397,9 +410,13 @@ def run_b200(args):
     }
     print(json.dumps(line), flush=True)
   if world > 1:
-    import torch.distributed as dist
-
-    dist.destroy_process_group()
+    # CUDA graphs that captured NCCL collectives keep the communicator busy at teardown
+    # (destroy_process_group was seen to hang); everything is measured and printed: leave hard.
+    torch.cuda.synchronize(dev)
+    barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():
