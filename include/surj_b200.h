@@ -164,6 +164,15 @@ int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, const float*
 int surj_adam_step(SurjStream stream, float* params, const float* grads, float* mu, float* nu, int32_t* count,
                    int64_t n, float lr, float b1, float b2, float eps, float grad_scale);
 
+/* --- one training step = the jitted `step` of examples/coupling_inference_surjection.py:81-90:
+ * loss = g_scale * sum(lp) (g_scale = -1: the examples' -sum; -1/B: the notebooks' -mean), its gradient
+ * w.r.t. params (left in g_params) and the optax.adam update of params / mu / nu / count.  On the fused
+ * executors the update is fused into the last stage of the gradient reduction (2 launches per step).
+ * Data-parallel callers use surj_chain_logprob_bwd + all-reduce + surj_adam_step instead. */
+int surj_train_step(const SurjPlan* plan, SurjStream stream, const float* y, const float* x, float* params,
+                    float g_scale, float* g_params, float* mu, float* nu, int32_t* count, float lr, float b1, float b2,
+                    float eps, float* loss_out, void* workspace, size_t workspace_bytes, int64_t batch);
+
 /* --- helpers */
 /* TFP _make_dense_autoregressive_masks restated; writes n_hidden+1 masks ([in, out] row-major,
  * bytes 0/1) back to back into out (size queried by passing out == NULL). */

@@ -100,6 +100,9 @@ _SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
   "surj_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
+  "surj_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
   "surj_made_masks": (C.c_int64, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8)]),
   "surj_permutation_inverse": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
   "surj_bench_fp32_peak": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]),

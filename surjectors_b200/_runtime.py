@@ -121,6 +121,20 @@ class Plan:
     return gp, gy, gx, lp
 
 
+def _plan_train_step(self, y, x, flat, g_scale, grads, opt, loss_out):
+  """surj_train_step: fused log_prob+VJP kernel, gradient reduction with the Adam update in its last stage."""
+  B = y.shape[0]
+  _check_inputs(self, y, x, flat)
+  ws, n = self.workspace(B, True, y.device)
+  st = self._lib.surj_train_step(
+    self._h, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), float(g_scale), grads.data_ptr(), opt.mu.data_ptr(),
+    opt.nu.data_ptr(), opt.count.data_ptr(), opt.lr, opt.b1, opt.b2, opt.eps, _ptr(loss_out), ws.data_ptr(), n, B)
+  _abi.check(st, "surj_train_step")
+
+
+Plan.train_step = _plan_train_step
+
+
 def _ptr(t):
   return None if t is None else t.data_ptr()
 

@@ -361,6 +361,7 @@ static int fused_grid(const SurjPlan* p, int64_t B, bool backward) {
   return (int)(tiles < cap ? tiles : cap);
 }
 static int fused_npad(const SurjPlan* p) { return (int)((p->n_params + 1 + 3) / 4 * 4); }
+static size_t fused_bwd_workspace(int64_t rows, int npad, int np);
 
 extern "C" size_t surj_plan_workspace_bytes(const SurjPlan* plan, int64_t batch, int32_t backward) {
   if (!plan || batch <= 0) return 0;
@@ -373,7 +374,7 @@ extern "C" size_t surj_plan_workspace_bytes(const SurjPlan* plan, int64_t batch,
       const int64_t tiles = (batch + plan->fused->nt - 1) / plan->fused->nt;
       rows = tiles < 4096 ? tiles : 4096;
     }
-    return (size_t)rows * fused_npad(plan) * sizeof(float);
+    return fused_bwd_workspace(rows, fused_npad(plan), (int)plan->n_params);
   }
   return vm_global_workspace_bytes(plan->vmp, batch, backward != 0);
 }
@@ -410,7 +411,7 @@ extern "C" int surj_chain_logprob_fwd(const SurjPlan* plan, SurjStream stream, c
     r = ensure_device(plan);
     if (r) return r;
     return vm_launch(plan->vmp, st, false, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, nullptr, 0.0f, nullptr,
-                     z_out, lp_out, nullptr, nullptr, nullptr, 0, batch, fused_grid(plan, batch, false));
+                     z_out, lp_out, nullptr, nullptr, nullptr, 0, batch, fused_grid(plan, batch, false), nullptr, 0);
   }
   if (plan->exec == 1) {
     r = ensure_device(plan);
@@ -426,33 +427,117 @@ extern "C" int surj_chain_logprob_fwd(const SurjPlan* plan, SurjStream stream, c
                        z_out, lp_out, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, batch);
 }
 
-// grads[p] = sum_rows partials[row][p]; column np carries sum(lp) -> loss = scale * sum(lp)
+// ---- gradient reduction (+ optional fused Adam) for the fused executors
+// Every CTA of the backward kernel leaves one partial row [npad] (column np = its sum of lp).
+// Level 1: grid (32-column blocks) x (RSL row slices); each CTA sums its rows in a fixed order and
+// stores one slice row.  Level 2: the last CTA of a column block to arrive (ticket) adds the RSL
+// slice rows in a fixed order -- the result is deterministic -- writes g_params / loss and, when asked,
+// applies the optax.adam update in the same pass.  The last CTA overall advances the step counter.
+// Tickets are zeroed by the backward kernel that precedes this one on the stream.
+struct AdamArgs {
+  float* params; float* mu; float* nu; int32_t* count;
+  float lr, b1, b2, eps;
+};
+constexpr int RSL = 8;
+
 __global__ void __launch_bounds__(256)
 surj_reduce_partials_kernel(const float* __restrict__ partials, int nrows, int npad, int np,
-                            float* __restrict__ g_params, float* __restrict__ loss_out, float loss_scale) {
+                            float* __restrict__ slices, unsigned* __restrict__ tickets,
+                            float* __restrict__ g_params, float* __restrict__ loss_out, float loss_scale, AdamArgs ad) {
   __shared__ float red[8][33];
+  __shared__ unsigned s_ticket;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
+  const int per = (nrows + RSL - 1) / RSL;
+  const int r0 = blockIdx.y * per, r1 = min(nrows, r0 + per);
   float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
   if (col <= np) {
-    int r = w;
-    for (; r + 24 < nrows; r += 32) {
+    int r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
       a0 += partials[(size_t)r * npad + col];
       a1 += partials[(size_t)(r + 8) * npad + col];
       a2 += partials[(size_t)(r + 16) * npad + col];
       a3 += partials[(size_t)(r + 24) * npad + col];
     }
-    for (; r < nrows; r += 8) a0 += partials[(size_t)r * npad + col];
+    for (; r < r1; r += 8) a0 += partials[(size_t)r * npad + col];
   }
   red[w][lane] = (a0 + a1) + (a2 + a3);
   __syncthreads();
-  if (w == 0 && col <= np) {
+  if (w == 0) {
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += red[k][lane];
-    if (col < np) g_params[col] = s;
-    else if (loss_out) *loss_out = loss_scale * s;
+    if (col <= np) slices[(size_t)blockIdx.y * npad + col] = s;
+    __threadfence();
+    if (lane == 0) s_ticket = atomicAdd(tickets + blockIdx.x, 1u);
+    __syncwarp();
+    if (s_ticket == RSL - 1) {  // last slice of this column block: finish the columns
+      __threadfence();
+      if (col <= np) {
+        float g = 0.0f;
+#pragma unroll
+        for (int k = 0; k < RSL; ++k) g += __ldcg(slices + (size_t)k * npad + col);
+        if (col < np) {
+          g_params[col] = g;
+          if (ad.params != nullptr) {  // optax.adam (examples/coupling_inference_surjection.py:78,88-89)
+            const int t = *ad.count + 1;
+            const float c1 = 1.0f / (1.0f - powf(ad.b1, (float)t)), c2 = 1.0f / (1.0f - powf(ad.b2, (float)t));
+            const float m = ad.b1 * ad.mu[col] + (1.0f - ad.b1) * g;
+            const float v = ad.b2 * ad.nu[col] + (1.0f - ad.b2) * g * g;
+            ad.mu[col] = m;
+            ad.nu[col] = v;
+            ad.params[col] -= ad.lr * (m * c1) / (sqrtf(v * c2) + ad.eps);
+          }
+        } else if (loss_out) {
+          *loss_out = loss_scale * g;
+        }
+      }
+      __threadfence();
+      if (lane == 0) {
+        const unsigned done = atomicAdd(tickets + gridDim.x, 1u);
+        if (done == gridDim.x - 1 && ad.params != nullptr) *ad.count += 1;  // every column block has read count
+      }
+    }
   }
+}
+
+static size_t fused_bwd_workspace(int64_t rows, int npad, int np) {
+  const size_t ncb = (size_t)(np + 1 + 31) / 32;
+  return ((size_t)rows + RSL) * npad * sizeof(float) + (ncb + 1 + 3) / 4 * 4 * sizeof(unsigned);
+}
+
+static int fused_backward(const SurjPlan* plan, cudaStream_t st, const float* y, const float* x, const float* params,
+                          const float* g_lp, float g_scale, const float* g_z, float* g_params, float* loss_out,
+                          float* lp_out, float* g_y, float* g_x, void* workspace, size_t workspace_bytes, int64_t batch,
+                          AdamArgs ad) {
+  int r = ensure_device(plan);
+  if (r) return r;
+  const int grid = fused_grid(plan, batch, true);
+  const int npad = fused_npad(plan);
+  const int np = (int)plan->n_params;
+  if (!workspace || workspace_bytes < fused_bwd_workspace(grid, npad, np) || ((uintptr_t)workspace & 15u)) {
+    surj_set_error("workspace too small or misaligned for the backward pass");
+    return SURJ_E_WORKSPACE;
+  }
+  float* partials = (float*)workspace;
+  float* slices = partials + (size_t)grid * npad;
+  unsigned* tickets = (unsigned*)(slices + (size_t)RSL * npad);
+  const int ncb = (np + 1 + 31) / 32;
+  const int with_base = plan->base == SURJ_BASE_STANDARD_NORMAL;
+  if (plan->exec == 2) {
+    r = vm_launch(plan->vmp, st, true, with_base, y, x, params, g_lp, g_scale, g_z, nullptr, lp_out, g_y, g_x, partials,
+                  npad, batch, grid, tickets, ncb + 1);
+    if (r) return r;
+  } else {
+    cudaError_t e = plan->fused->bwd(grid, st, with_base, y, x, params, g_lp, g_scale, g_z, partials, npad, lp_out,
+                                     nullptr, g_y, g_x, batch, tickets, ncb + 1);
+    if (e != cudaSuccess) return surj_cuda_fail(e, "chain_bwd_kernel launch");
+  }
+  surj_reduce_partials_kernel<<<dim3(ncb, RSL), 256, 0, st>>>(partials, grid, npad, np, slices, tickets, g_params,
+                                                             loss_out, g_lp ? 1.0f : g_scale, ad);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return surj_cuda_fail(e, "reduce_partials launch");
+  return SURJ_OK;
 }
 
 extern "C" int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, const float* y, const float* x,
@@ -466,34 +551,9 @@ extern "C" int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, c
     return SURJ_E_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan->exec == 1 || plan->exec == 2) {
-    r = ensure_device(plan);
-    if (r) return r;
-    const int grid = fused_grid(plan, batch, true);
-    const int npad = fused_npad(plan);
-    const size_t need = (size_t)grid * npad * sizeof(float);
-    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15u)) {
-      surj_set_error("workspace too small or misaligned for the backward pass");
-      return SURJ_E_WORKSPACE;
-    }
-    float* partials = (float*)workspace;
-    cudaError_t e;
-    if (plan->exec == 2) {
-      r = vm_launch(plan->vmp, st, true, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z,
-                    nullptr, lp_out, g_y, g_x, partials, npad, batch, grid);
-      if (r) return r;
-    } else {
-      e = plan->fused->bwd(grid, st, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z,
-                           partials, npad, lp_out, nullptr, g_y, g_x, batch);
-      if (e != cudaSuccess) return surj_cuda_fail(e, "chain_bwd_kernel launch");
-    }
-    const int np = (int)plan->n_params;
-    surj_reduce_partials_kernel<<<(np + 1 + 31) / 32, 256, 0, st>>>(partials, grid, npad, np, g_params, loss_out,
-                                                                    g_lp ? 1.0f : g_scale);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return surj_cuda_fail(e, "reduce_partials launch");
-    return SURJ_OK;
-  }
+  if (plan->exec == 1 || plan->exec == 2)
+    return fused_backward(plan, st, y, x, params, g_lp, g_scale, g_z, g_params, loss_out, lp_out, g_y, g_x, workspace,
+                          workspace_bytes, batch, AdamArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0});
   r = ensure_device(plan);
   if (r) return r;
   return vm_global_run(plan->vmp, st, true, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z,
@@ -537,6 +597,29 @@ extern "C" int surj_adam_step(SurjStream stream, float* params, const float* gra
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return surj_cuda_fail(e, "adam launch");
   return SURJ_OK;
+}
+
+// The whole jitted `step` of the reference's examples (examples/coupling_inference_surjection.py:81-90):
+// loss = -sum(lp) (g_scale = -1) or -mean, value_and_grad, optax.adam update -- for the fused executors
+// two launches (backward kernel; gradient reduction with the Adam update fused into its last stage).
+extern "C" int surj_train_step(const SurjPlan* plan, SurjStream stream, const float* y, const float* x, float* params,
+                               float g_scale, float* g_params, float* mu, float* nu, int32_t* count, float lr, float b1,
+                               float b2, float eps, float* loss_out, void* workspace, size_t workspace_bytes,
+                               int64_t batch) {
+  int r = check_io(plan, y, x, params, batch);
+  if (r) return r;
+  if (!g_params || !mu || !nu || !count) {
+    surj_set_error("surj_train_step: g_params, mu, nu and count are required");
+    return SURJ_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->exec == 1 || plan->exec == 2)
+    return fused_backward(plan, st, y, x, params, nullptr, g_scale, nullptr, g_params, loss_out, nullptr, nullptr,
+                          nullptr, workspace, workspace_bytes, batch, AdamArgs{params, mu, nu, count, lr, b1, b2, eps});
+  r = surj_chain_logprob_bwd(plan, stream, y, x, params, nullptr, g_scale, nullptr, g_params, loss_out, nullptr, nullptr,
+                             nullptr, workspace, workspace_bytes, batch);
+  if (r) return r;
+  return surj_adam_step(stream, params, g_params, mu, nu, count, plan->n_params, lr, b1, b2, eps, 1.0f);
 }
 
 // ------------------------------------------------------------- FP32 peak probe

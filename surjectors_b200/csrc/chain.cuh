@@ -168,11 +168,13 @@ chain_bwd_kernel(int with_base, const float* __restrict__ y, const float* __rest
                  const float* __restrict__ params, const float* __restrict__ g_lp, float g_scale,
                  const float* __restrict__ g_z, float* __restrict__ partials, int npad,
                  float* __restrict__ lp_out, float* __restrict__ z_out, float* __restrict__ g_y,
-                 float* __restrict__ g_x_out, long long B) {
+                 float* __restrict__ g_x_out, long long B, unsigned* __restrict__ tickets, int n_tickets) {
   extern __shared__ __align__(16) float smem[];
   float* sp = smem;
   float* scr = sp + CH::NP4;
-  float* sg = scr + CH::NSCR4;             // [NP4 + 4]: gradient accumulator, slot NP = sum lp
+  float* sg = scr + CH::NSCR4;
+  if (blockIdx.x == 0)  // arm the tickets of the gradient-reduction kernel that follows on the stream
+    for (int i = threadIdx.x; i < n_tickets; i += NT) tickets[i] = 0u;             // [NP4 + 4]: gradient accumulator, slot NP = sum lp
   float* tile = sg + CH::NP4 + 4;
   const int tid = threadIdx.x;
   stage_params<CH::NP4>(sp, params, CH::NP, tid, NT);
@@ -246,9 +248,10 @@ struct SmallLaunch {
   }
   static cudaError_t bwd(int grid, cudaStream_t st, int with_base, const float* y, const float* x,
                          const float* params, const float* g_lp, float g_scale, const float* g_z, float* partials,
-                         int npad, float* lp, float* z, float* g_y, float* g_x, long long B) {
+                         int npad, float* lp, float* z, float* g_y, float* g_x, long long B, unsigned* tickets,
+                         int n_tickets) {
     chain_bwd_kernel<CH, NT, MINB><<<grid, NT, BWD_SMEM, st>>>(with_base, y, x, params, g_lp, g_scale, g_z, partials, npad, lp,
-                                                         z, g_y, g_x, B);
+                                                               z, g_y, g_x, B, tickets, n_tickets);
     return cudaGetLastError();
   }
   static SmallKernels make() {

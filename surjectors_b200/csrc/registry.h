@@ -11,7 +11,7 @@ struct SmallKernels {
                      float* z, float* lp, long long B);
   cudaError_t (*bwd)(int grid, cudaStream_t st, int with_base, const float* y, const float* x, const float* params,
                      const float* g_lp, float g_scale, const float* g_z, float* partials, int npad, float* lp,
-                     float* z, float* g_y, float* g_x, long long B);
+                     float* z, float* g_y, float* g_x, long long B, unsigned* tickets, int n_tickets);
 };
 
 void surj_register_small(unsigned long long key, SmallKernels k, const char* name);

@@ -135,11 +135,14 @@ VM_DEV void op_linear_dw(Ctx<NT, S>& c, float* __restrict__ grad, const Op& op) 
 
 template <int NT, int S>
 __global__ void __launch_bounds__(NT)
-vm_kernel(Program P, Io io, const float* __restrict__ params, float* __restrict__ partials, int npad, long long B) {
+vm_kernel(Program P, Io io, const float* __restrict__ params, float* __restrict__ partials, int npad, long long B,
+          unsigned* __restrict__ tickets, int n_tickets) {
   constexpr int T = NT * S;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int backward = io.backward;
+  if (blockIdx.x == 0)  // arm the tickets of the gradient-reduction kernel that follows on the stream
+    for (int i = tid; i < n_tickets; i += NT) tickets[i] = 0u;
   const int n_ops = backward ? P.n_ops_bwd : P.n_ops_fwd;
   // carve shared memory (every region 16-byte aligned)
   auto align4 = [](int n) { return (n + 3) & ~3; };

@@ -574,7 +574,7 @@ void vm_destroy(VmPlan* v) {
   delete v;
 }
 
-typedef void (*VmKernel)(vm::Program, vm::Io, const float*, float*, int, long long);
+typedef void (*VmKernel)(vm::Program, vm::Io, const float*, float*, int, long long, unsigned*, int);
 static VmKernel vm_kernel_for(int nt, int s) {
   if (nt == 64 && s == 1) return vm::vm_kernel<64, 1>;
   if (nt == 32 && s == 1) return vm::vm_kernel<32, 1>;
@@ -658,14 +658,16 @@ int vm_max_grid(const VmPlan* v, int64_t B) {  // upper bound usable before a de
 
 int vm_launch(VmPlan* v, cudaStream_t st, bool backward, int with_base, const float* y, const float* x,
               const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
-              float* g_y, float* g_x, float* partials, int npad, int64_t B, int grid) {
+              float* g_y, float* g_x, float* partials, int npad, int64_t B, int grid, unsigned* tickets,
+              int n_tickets) {
   vm::Program P = v->prog;
   P.ops = backward ? v->d_ops_bwd : v->d_ops_fwd;
   vm::Io io;
   io.y = y; io.x = x; io.g_lp = g_lp; io.g_z = g_z; io.z_out = z_out; io.lp_out = lp_out; io.g_y = g_y; io.g_x = g_x;
   io.g_scale = g_scale; io.with_base = with_base; io.backward = backward ? 1 : 0;
   VmKernel k = vm_kernel_for(v->nt, v->s);
-  k<<<grid, v->nt, backward ? v->smem_bwd : v->smem_fwd, st>>>(P, io, params, partials, npad, (long long)B);
+  k<<<grid, v->nt, backward ? v->smem_bwd : v->smem_fwd, st>>>(P, io, params, partials, npad, (long long)B, tickets,
+                                                                n_tickets);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return surj_cuda_fail(e, "vm_kernel launch");
   return SURJ_OK;

@@ -66,14 +66,19 @@ class TrainStep:
     return self.grads[self.flat.numel():self.flat.numel() + 1]
 
   def launches_per_step(self):
+    if self.world == 1 and self.plan.is_fused:
+      return 2
     return self.plan.launches(backward=True) + 2 + (1 if self.world > 1 else 0)
 
   def step(self, y, x=None):
     n = self.flat.numel()
     B = y.shape[0]
     g_scale = -1.0 if self.reduction == "sum" else -1.0 / (B * self.world)
-    self.plan.bwd(y, x if self.plan.dim_x > 0 else None, self.flat, g_lp=None, g_scale=g_scale,
-                  g_params=self.grads, loss_out=self.grads[n:n + 1])
+    xx = x if self.plan.dim_x > 0 else None
+    if self.world == 1:  # the whole step is two launches: backward kernel, reduction + Adam
+      self.plan.train_step(y, xx, self.flat, g_scale, self.grads, self.opt, self.grads[n:n + 1])
+      return self.loss
+    self.plan.bwd(y, xx, self.flat, g_lp=None, g_scale=g_scale, g_params=self.grads, loss_out=self.grads[n:n + 1])
     if self.world > 1:
       parallel.allreduce_flat_(self.grads, self.group)  # the one collective of the path: flat gradient + loss
     self.opt.update_(self.flat, self.grads)
