@@ -233,7 +233,12 @@ class Linear(Module):
     return out
 
 
+relu_probe = None  # tests set this to a list to collect, per sample, min |pre-activation| of every ReLU call
+
+
 def relu(x):
+  if relu_probe is not None and x.dim() == 2:
+    relu_probe.append(x.detach().abs().min(dim=-1).values)
   return torch.relu(x)
 
 

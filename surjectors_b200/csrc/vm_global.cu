@@ -10,10 +10,12 @@
 // masked / transposed once per call by vg_stage into the workspace (the staging table of the plan).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "plan.h"
 #include "vm_ops.cuh"
 #include "vm_plan.h"
+#include "vm_tc.cuh"
 
 namespace vm {
 
@@ -273,6 +275,19 @@ int vm_global_run(VmPlan* v, cudaStream_t st, bool backward, int with_base, cons
                   float* g_y, float* g_x, float* g_params, float* loss_out, void* ws, size_t ws_bytes, int64_t B) {
   const int C = chunk_cols(B, v->n_rows);
   Carve k = carve(v, ws, C, backward);
+  static const int tc_mode = [] {
+    const char* e = getenv("SURJ_B200_TC");  // 0: FP32 SIMT tiles only; 2: tcgen05 for LINEAR only; 3: for LINEAR_DW only
+    return e ? atoi(e) : 1;
+  }();
+  const bool use_tc_lin = tc_mode == 1 || tc_mode == 2, use_tc_dw = tc_mode == 1 || tc_mode == 3;
+  static const bool use_tc = [] {
+    const bool on = true;
+    if (on) {
+      cudaFuncSetAttribute(vmtc::vg_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::SMEM_BYTES);
+      cudaFuncSetAttribute(vmtc::vg_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::SMEM_BYTES);
+    }
+    return on;
+  }();
   if (!ws || ws_bytes < k.total || ((uintptr_t)ws & 255u)) {
     surj_set_error("workspace too small or not 256-byte aligned for the per-layer path");
     return SURJ_E_WORKSPACE;
@@ -296,14 +311,25 @@ int vm_global_run(VmPlan* v, cudaStream_t st, bool backward, int with_base, cons
     while (pc < ops.size()) {
       const vm::Op& op = ops[pc];
       if (op.code == vm::OP_LINEAR) {
-        dim3 grid(cols / vm::LBM, (op.a[5] + vm::LBN - 1) / vm::LBN);
-        vm::vg_linear<<<grid, 256, 0, st>>>(op, k.rows, C, k.par);
+        if (use_tc && use_tc_lin && op.a[1] >= 32 && op.a[5] >= 32) {  // tcgen05 3xTF32 tiles for real contractions
+          dim3 grid(cols / vmtc::TM, (op.a[5] + vmtc::TN - 1) / vmtc::TN);
+          vmtc::vg_linear_tc<<<grid, 128, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, k.par);
+        } else {
+          dim3 grid(cols / vm::LBM, (op.a[5] + vm::LBN - 1) / vm::LBN);
+          vm::vg_linear<<<grid, 256, 0, st>>>(op, k.rows, C, k.par);
+        }
         ++pc;
       } else if (op.code == vm::OP_LINEAR_DW) {
         const int NA = op.a[1] + (op.a[6] >= 0 ? 1 : 0), NG = op.a[3];
-        const int slab = 2048;
-        dim3 grid((NA + vm::DBI - 1) / vm::DBI, (NG + vm::DBJ - 1) / vm::DBJ, (cols + slab - 1) / slab);
-        vm::vg_dw<<<grid, 256, 0, st>>>(op, k.rows, C, cols, slab, k.grad);
+        if (use_tc && use_tc_dw && NA >= 32 && NG >= 32) {
+          const int slab = 4096;
+          dim3 grid((NA + vmtc::TM - 1) / vmtc::TM, (NG + vmtc::TN - 1) / vmtc::TN, (cols + slab - 1) / slab);
+          vmtc::vg_dw_tc<<<grid, 128, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, cols, slab, k.grad);
+        } else {
+          const int slab = 2048;
+          dim3 grid((NA + vm::DBI - 1) / vm::DBI, (NG + vm::DBJ - 1) / vm::DBJ, (cols + slab - 1) / slab);
+          vm::vg_dw<<<grid, 256, 0, st>>>(op, k.rows, C, cols, slab, k.grad);
+        }
         ++pc;
       } else {
         size_t e = pc;

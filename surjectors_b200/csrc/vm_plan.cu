@@ -100,9 +100,16 @@ Op mk(int code, std::initializer_list<int> a, float f0 = 0.0f, float f1 = 0.0f) 
   o.f0 = f0; o.f1 = f1;
   return o;
 }
-Op linear(int in_row, int n_in, int w_off, int ld, int out_row, int n_out_pad, int b_off, int act, int accumulate,
-          int pre_row) {
-  return mk(vm::OP_LINEAR, {in_row, n_in, w_off, ld, out_row, n_out_pad, b_off, act, accumulate, pre_row});
+// out = act(b + in W): a10 / a11 locate the [out][in] copy of the same weights (what the tensor-core
+// kernel stages as its K-major B operand), a12 = number of real (unpadded) outputs
+Op lin_fwd(const Mat& m, int in_row, int out_row, int act, int accumulate, int pre_row) {
+  return mk(vm::OP_LINEAR, {in_row, m.n_in, m.w_off, m.ld, out_row, m.ld, m.b_off, act, accumulate, pre_row, m.wt_off,
+                            m.ldt, m.n_out});
+}
+// g_in = g W^T: an OP_LINEAR on the transposed copy (whose [out][in] copy is the primary matrix)
+Op lin_bwd_in(const Mat& m, int g_row, int dst_row, int accumulate) {
+  return mk(vm::OP_LINEAR, {g_row, m.n_out, m.wt_off, m.ldt, dst_row, m.ldt, -1, vm::ACT_IDENTITY, accumulate, -1, m.w_off,
+                            m.ld, m.n_in});
 }
 
 // ----- MLP (hk.nets.MLP / Linear stack) with optional row / column compaction of its first / last layer
@@ -135,7 +142,7 @@ std::vector<NetRows> emit_mlp_fwd(Builder& B, std::vector<Op>& ops, const std::v
     r.in_row = cur; r.n_in = m.n_in; r.act = acts[l]; r.m = m;
     r.post_row = B.scratch(m.ld);
     r.pre_row = (train && r.act != vm::ACT_IDENTITY) ? B.scratch(m.ld) : -1;
-    ops.push_back(linear(cur, m.n_in, m.w_off, m.ld, r.post_row, m.ld, m.b_off, r.act, 0, r.pre_row));
+    ops.push_back(lin_fwd(m, cur, r.post_row, r.act, 0, r.pre_row));
     rows.push_back(r);
     cur = r.post_row;
   }
@@ -152,8 +159,7 @@ void emit_mlp_bwd(std::vector<Op>& ops, const std::vector<NetRows>& rows, bool n
     ops.push_back(mk(vm::OP_LINEAR_DW, {r.in_row, r.n_in, r.post_row, r.m.n_out, r.m.w_off, r.m.ld, r.m.b_off}));
     if (l > 0 || need_gin0) {
       const bool acc = (l == 0 && gin0_row >= 0);
-      ops.push_back(linear(r.post_row, r.m.n_out, r.m.wt_off, r.m.ldt, acc ? gin0_row : r.in_row, r.m.ldt, -1,
-                           vm::ACT_IDENTITY, acc ? 1 : 0, -1));
+      ops.push_back(lin_bwd_in(r.m, r.post_row, acc ? gin0_row : r.in_row, acc ? 1 : 0));
     }
   }
 }
@@ -392,11 +398,10 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
           if (mm.has_ctx) {
             R.cc_row = B.scratch(pad8(ctxw));
             ops.push_back(mk(vm::OP_GATHER, {R.cc_row, ctxw, B.tab(csrc)}));
-            ops.push_back(linear(Ein, Dm, mm.l0.w_off, mm.l0.ld, R.p0_row, mm.l0.ld, mm.l0.b_off, vm::ACT_IDENTITY, 0, -1));
-            ops.push_back(linear(R.cc_row, ctxw, mm.ctx.w_off, mm.ctx.ld, R.h0_row, mm.ctx.ld, mm.ctx.b_off, act, 1,
-                                 R.p0_row));
+            ops.push_back(lin_fwd(mm.l0, Ein, R.p0_row, vm::ACT_IDENTITY, 0, -1));
+            ops.push_back(lin_fwd(mm.ctx, R.cc_row, R.h0_row, act, 1, R.p0_row));
           } else {
-            ops.push_back(linear(Ein, Dm, mm.l0.w_off, mm.l0.ld, R.h0_row, mm.l0.ld, mm.l0.b_off, act, 0, R.p0_row));
+            ops.push_back(lin_fwd(mm.l0, Ein, R.h0_row, act, 0, R.p0_row));
           }
           R.rest = emit_mlp_fwd(B, ops, mm.rest, mm.rest_acts.data(), R.h0_row, train);
         };
@@ -435,11 +440,10 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
           if (act != vm::ACT_IDENTITY) C.bwd.push_back(mk(vm::OP_ACT_BWD, {R.h0_row, R.p0_row, mm.l0.n_out, act}));
           C.bwd.push_back(mk(vm::OP_LINEAR_DW, {Ein, Dm, R.h0_row, mm.l0.n_out, mm.l0.w_off, mm.l0.ld, mm.l0.b_off}));
           // g_y += g_pre0 W0^T, accumulated straight into the cotangent rows AFFINE_BWD just wrote
-          C.bwd.push_back(linear(R.h0_row, mm.l0.n_out, mm.l0.wt_off, mm.l0.ldt, Gin, mm.l0.ldt, -1, vm::ACT_IDENTITY, 1, -1));
+          C.bwd.push_back(lin_bwd_in(mm.l0, R.h0_row, Gin, 1));
           if (mm.has_ctx) {
             C.bwd.push_back(mk(vm::OP_LINEAR_DW, {R.cc_row, ctxw, R.h0_row, mm.ctx.n_out, mm.ctx.w_off, mm.ctx.ld, mm.ctx.b_off}));
-            C.bwd.push_back(linear(R.h0_row, mm.ctx.n_out, mm.ctx.wt_off, mm.ctx.ldt, R.cc_row, mm.ctx.ldt, -1,
-                                   vm::ACT_IDENTITY, 0, -1));
+            C.bwd.push_back(lin_bwd_in(mm.ctx, R.h0_row, R.cc_row, 0));
             if (funnel) {
               C.bwd.push_back(mk(vm::OP_ADD, {Gin + K, R.cc_row, D - K}));
               if (dxu) C.bwd.push_back(mk(vm::OP_ADD, {GX, R.cc_row + (D - K), dxu}));
@@ -495,17 +499,17 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
         {
           B.scratch_reset();
           const int t = B.scratch(pad8(n));
-          C.fwd.push_back(linear(Ein, n, U.w_off, U.ld, t, U.ld, -1, vm::ACT_IDENTITY, 0, -1));
-          C.fwd.push_back(linear(t, n, Lm.w_off, Lm.ld, Eout, Lm.ld, -1, vm::ACT_IDENTITY, 0, -1));
+          C.fwd.push_back(lin_fwd(U, Ein, t, vm::ACT_IDENTITY, 0, -1));
+          C.fwd.push_back(lin_fwd(Lm, t, Eout, vm::ACT_IDENTITY, 0, -1));
           C.fwd.push_back(mk(vm::OP_ADD_SCALAR, {slot}));
         }
         {
           B.scratch_reset();
           const int t = B.scratch(pad8(n)), gt = B.scratch(pad8(n));
-          C.train.push_back(linear(Ein, n, U.w_off, U.ld, t, U.ld, -1, vm::ACT_IDENTITY, 0, -1));
-          C.bwd.push_back(linear(Gout, n, Lm.wt_off, Lm.ldt, gt, Lm.ldt, -1, vm::ACT_IDENTITY, 0, -1));  // g_t = g_z L^T
+          C.train.push_back(lin_fwd(U, Ein, t, vm::ACT_IDENTITY, 0, -1));
+          C.bwd.push_back(lin_bwd_in(Lm, Gout, gt, 0));                                                    // g_t = g_z L^T
           C.bwd.push_back(mk(vm::OP_LINEAR_DW, {t, n, Gout, n, Lm.w_off, Lm.ld, -1}));                     // g_L = t^T g_z
-          C.bwd.push_back(linear(gt, n, U.wt_off, U.ldt, Gin, U.ldt, -1, vm::ACT_IDENTITY, 0, -1));        // g_y = g_t U^T
+          C.bwd.push_back(lin_bwd_in(U, gt, Gin, 0));                                                      // g_y = g_t U^T
           C.bwd.push_back(mk(vm::OP_LINEAR_DW, {Ein, n, gt, n, U.w_off, U.ld, -1}));                       // g_U = y^T g_t
           C.bwd.push_back(mk(vm::OP_SCALAR_BWD, {slot}));
         }

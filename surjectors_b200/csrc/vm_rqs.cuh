@@ -25,6 +25,7 @@ namespace vm {
 struct RqsBin {
   int bin;                        // selected bin, -1 = below range, K = above range
   float x0, x1, y0, y1, d0, d1;   // knots / slopes of the bin (tails: d0 = d1 = the boundary slope)
+  float bw, bh;                   // width / height of the bin, taken from the softmax directly (no knot cancellation)
   float mw, mh, zw, zh;           // softmax max and normaliser of widths / heights
   float pw_cum, pw_bin, ph_cum, ph_bin;  // softmax mass before the bin and of the bin
 };
@@ -51,32 +52,49 @@ VM_DEV void rqs_locate(const Th& th, int K, float lo, float hi, float v, bool fo
     b.bin = -1;
     b.d0 = b.d1 = rqs_slope(th(2 * K));
     b.x0 = b.x1 = b.y0 = b.y1 = lo;
+    b.bw = b.bh = 1.0f;
     return;
   }
   if (v >= hi) {
     b.bin = K;
     b.d0 = b.d1 = rqs_slope(th(3 * K));
     b.x0 = b.x1 = b.y0 = b.y1 = hi;
+    b.bw = b.bh = 1.0f;
     return;
   }
   const float span = (hi - lo) - (float)K * VM_RQS_MIN_BIN;
   const float iw = 1.0f / zw, ih = 1.0f / zh;
-  float xk = lo, yk = lo, cw = 0.0f, ch = 0.0f, cpw = 0.0f, cph = 0.0f;
+  // knot positions = lo + running sum of the bin sizes; the sum is Kahan-compensated because a
+  // position error is amplified by 1 / bin_width in (v - x_k) / bw
+  float xk = lo, yk = lo, cw = 0.0f, ch = 0.0f, ew = 0.0f, eh = 0.0f, cpw = 0.0f, cph = 0.0f;
   int bin = -2;
   for (int k = 0; k < K; ++k) {
     const float pw = expf(th(k) - mw) * iw, ph = expf(th(K + k) - mh) * ih;
-    cw += pw * span + VM_RQS_MIN_BIN;
-    ch += ph * span + VM_RQS_MIN_BIN;
+    const float wk = pw * span + VM_RQS_MIN_BIN, hk = ph * span + VM_RQS_MIN_BIN;
+    {
+      const float yv = wk - ew, t = cw + yv;
+      ew = (t - cw) - yv;
+      cw = t;
+    }
+    {
+      const float yv = hk - eh, t = ch + yv;
+      eh = (t - ch) - yv;
+      ch = t;
+    }
     const float xn = (k == K - 1) ? hi : lo + cw;
     const float yn = (k == K - 1) ? hi : lo + ch;
     const float p0 = forward ? xk : yk, p1 = forward ? xn : yn;
     if (bin == -2 && ((v >= p0 && v < p1) || (k == 0 && !(v == v)))) {  // NaN: first bin, like distrax
       bin = k;
       b.x0 = xk; b.x1 = xn; b.y0 = yk; b.y1 = yn;
+      b.bw = (k == K - 1) ? hi - xk : wk;
+      b.bh = (k == K - 1) ? hi - yk : hk;
       b.pw_cum = cpw; b.pw_bin = pw; b.ph_cum = cph; b.ph_bin = ph;
     }
     if (k == 0 && bin == -2) {  // remember bin 0 as the "no bin matched" fallback of distrax
       b.x0 = xk; b.x1 = xn; b.y0 = yk; b.y1 = yn;
+      b.bw = (K == 1) ? hi - xk : wk;
+      b.bh = (K == 1) ? hi - yk : hk;
       b.pw_bin = pw; b.ph_bin = ph;
     }
     xk = xn; yk = yn; cpw += pw; cph += ph;
@@ -95,7 +113,7 @@ VM_DEV void rqs_eval(const RqsBin& b, int K, float lo, float hi, float v, bool f
     else { out = (v - e) / b.d0 + e; ld = -logf(b.d0); }
     return;
   }
-  const float bw = b.x1 - b.x0, bh = b.y1 - b.y0;
+  const float bw = b.bw, bh = b.bh;
   const float s = bh / bw;
   const float t = b.d1 + b.d0 - 2.0f * s;
   float z;
@@ -136,7 +154,7 @@ VM_DEV float rqs_bwd(Th& th, int K, float lo, float hi, float v, bool forward, f
     th(ks) = gd * rqs_sigmoid(us + VM_RQS_SLOPE_OFFSET);
     return g_v;
   }
-  const float bw = b.x1 - b.x0, bh = b.y1 - b.y0;
+  const float bw = b.bw, bh = b.bh;
   const float s = bh / bw;
   const float t = b.d1 + b.d0 - 2.0f * s;
   float gs, gt, gbw, gbh;

@@ -1,0 +1,319 @@
+// tcgen05 (5th-gen tensor core) matrix products of the per-op executor, FP32-grade via 3xTF32.
+//
+//   D[m][n] = sum_k A[m][k] * B[n][k]        M tile = 128 (TMEM lanes), N tile <= 256 (TMEM columns)
+//
+// issued as tcgen05.mma.cta_group::1.kind::tf32 by ONE thread, operands in shared memory in the
+// canonical K-major no-swizzle ("interleave") UMMA layout, accumulator in TMEM, read back with
+// tcgen05.ld for the epilogue.  Every fp32 operand x is split into hi = tf32(x) and
+// lo = tf32(x - hi) while it is staged, and each K step issues lo*hi + hi*lo + hi*hi, which keeps the
+// product error near 2^-21 relative -- the 1e-5 / 1e-4 parity bounds rule out plain TF32 (2^-11).
+// The tensor core's accumulator add truncates, which shows up as a systematic bias once hundreds
+// of K steps are chained (measured: 1.7e-5 on the 16-layer MADE config); so only ONE K block (32) is
+// accumulated inside the tensor core, into one of two TMEM buffers, and the blocks are summed in
+// FP32 registers with round-to-nearest adds while the next block's MMAs run.
+//
+// Two instantiations (vm_global.cu):
+//   LINEAR     out[j][s] = act(b[j] + sum_i W[i][j] in[i][s])   M = samples, N = outputs, K = inputs
+//              A = activations rows [i][s] (staged with a transpose), B = the [j][i] copy of W
+//   LINEAR_DW  grad[i][j] += sum_s in[i][s] g[j][s]             M = inputs (+ ones row), N = outputs,
+//              K = samples: both operands are K-major as stored (the [row][sample] layout)
+//
+// Shared-memory operand tile, K block of 32 floats: element (r, k) lives at byte
+//   (r / 8) * 1024 + (k / 4) * 128 + (r % 8) * 16 + (k % 4) * 4
+// i.e. 8x(16 B) core matrices, K-adjacent core matrices 128 B apart (LBO), 8-row groups 1024 B apart
+// (SBO); one MMA (K = 8 tf32) consumes two K-adjacent core matrices, so stepping K by 8 adds 256 B
+// to the descriptor start address.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vm.cuh"
+
+namespace vmtc {
+
+constexpr int TM = 128;      // M tile (TMEM lanes)
+constexpr int TN = 128;      // max N tile; two TMEM accumulator buffers of TN columns
+constexpr int BK = 32;       // K block staged per round
+constexpr int A_TILE = TM * BK;  // floats
+constexpr int B_TILE = TN * BK;
+constexpr size_t SMEM_BYTES = (size_t)(2 * A_TILE + 2 * B_TILE) * 4 + 1024 + 64;
+constexpr int TMEM_COLS = 2 * TN;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ int tile_off(int r, int k) {  // float offset of element (r, k) inside an operand tile
+  return (r >> 3) * 256 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  // start address (>>4) | LBO = 128 B (>>4 = 8) at bit 16 | SBO = 1024 B (>>4 = 64) at bit 32 | version 1 at bit 46
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | (64ull << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct Smem {
+  float* a_hi; float* a_lo; float* b_hi; float* b_lo;
+  uint64_t* bar;
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char* raw) {
+  uintptr_t p = ((uintptr_t)raw + 1023) & ~(uintptr_t)1023;
+  Smem s;
+  s.a_hi = (float*)p;
+  s.a_lo = s.a_hi + A_TILE;
+  s.b_hi = s.a_lo + A_TILE;
+  s.b_lo = s.b_hi + B_TILE;
+  s.bar = (uint64_t*)(s.b_lo + B_TILE);
+  s.tmem_slot = (uint32_t*)(s.bar + 2);
+  return s;
+}
+
+// split-store 4 consecutive-k values of row r into the hi / lo tiles (one 16-byte core-matrix row each)
+__device__ __forceinline__ void put4(float* hi, float* lo, int r, int k, float4 v) {
+  float4 h, l;
+  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+  l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+  const int o = tile_off(r, k);
+  *reinterpret_cast<float4*>(hi + o) = h;
+  *reinterpret_cast<float4*>(lo + o) = l;
+}
+
+// Operand whose source is K-major: src[(row0 + r) * pitch + k0 + k], r < n_rows (of `tile_rows`), k < 32.
+// Rows >= n_valid_rows and k >= k_valid are zero.  `special_row`/`special_src`: one row may come from
+// another base pointer (the ones row that carries the bias gradient).
+__device__ __forceinline__ void stage_kmajor(float* hi, float* lo, const float* __restrict__ src, size_t pitch,
+                                             int tile_rows, int n_valid_rows, int k_valid, int tid, int nthreads,
+                                             int special_row, const float* __restrict__ special_src) {
+  for (int idx = tid; idx < tile_rows * 8; idx += nthreads) {
+    const int r = idx >> 3, c4 = idx & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < n_valid_rows) {
+      const float* p = (r == special_row ? special_src : src + (size_t)r * pitch) + 4 * c4;
+      if (4 * c4 + 3 < k_valid) v = *reinterpret_cast<const float4*>(p);
+      else {
+        if (4 * c4 + 0 < k_valid) v.x = p[0];
+        if (4 * c4 + 1 < k_valid) v.y = p[1];
+        if (4 * c4 + 2 < k_valid) v.z = p[2];
+      }
+    }
+    put4(hi, lo, r, 4 * c4, v);
+  }
+}
+
+// Operand whose source is MN-major: src[(k0 + k) * pitch + row0 + r] (rows contiguous), 128 rows x 32 k.
+__device__ __forceinline__ void stage_transposed(float* hi, float* lo, const float* __restrict__ src, size_t pitch,
+                                                 int k_valid, int tid, int nthreads) {
+  // thread -> (row r = idx % 128, k group of 4 = idx / 128): coalesced along rows for every k
+  for (int idx = tid; idx < TM * 8; idx += nthreads) {
+    const int r = idx & (TM - 1), c4 = idx >> 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = src + (size_t)(4 * c4) * pitch + r;
+    if (4 * c4 + 0 < k_valid) v.x = p[0];
+    if (4 * c4 + 1 < k_valid) v.y = p[pitch];
+    if (4 * c4 + 2 < k_valid) v.z = p[2 * pitch];
+    if (4 * c4 + 3 < k_valid) v.w = p[3 * pitch];
+    put4(hi, lo, r, 4 * c4, v);
+  }
+}
+
+// acc[c] += TMEM buffer (this warp's 32 lanes, columns [0, n_tile))
+__device__ __forceinline__ void drain(uint32_t tmem_buf, int warp, int n_tile, float (&acc)[TN]) {
+#pragma unroll
+  for (int c0 = 0; c0 < TN; c0 += 32) {
+    if (c0 < n_tile) {
+      float v[32];
+      tmem_ld32(tmem_buf + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) acc[c0 + q] += v[q];
+    }
+  }
+}
+
+// K loop shared by both kernels.  Per K block: stage operands (hi / lo split) -> 12 MMAs into TMEM
+// buffer kb & 1 (fresh accumulator) -> commit; the previous block's buffer is drained into `acc`
+// while those MMAs run.  On return `acc` holds this thread's row (TMEM lane) of D.
+template <class StageA, class StageB>
+__device__ __forceinline__ void k_loop(const Smem& sm, uint32_t tmem_base, int n_tile, int K, int warp, StageA stage_a,
+                                       StageB stage_b, float (&acc)[TN]) {
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  const uint64_t da_hi = make_desc(smem_u32(sm.a_hi)), da_lo = make_desc(smem_u32(sm.a_lo));
+  const uint64_t db_hi = make_desc(smem_u32(sm.b_hi)), db_lo = make_desc(smem_u32(sm.b_lo));
+#pragma unroll
+  for (int c = 0; c < TN; ++c) acc[c] = 0.0f;
+  uint32_t parity[2] = {0u, 0u};
+  int kb = 0;
+  for (int k0 = 0; k0 < K; k0 += BK, ++kb) {
+    const int buf = kb & 1;
+    stage_a(k0, min(BK, K - k0));
+    stage_b(k0, min(BK, K - k0));
+    fence_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+    tc_fence_before();    // orders the tcgen05.ld of the previous drain before the MMAs that reuse that buffer
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(buf * TN);
+#pragma unroll
+      for (int ks = 0; ks < BK / 8; ++ks) {
+        const uint64_t adv = (uint64_t)(ks * 16);  // 256 B >> 4
+        mma_tf32(d, da_lo + adv, db_hi + adv, idesc, ks > 0 ? 1u : 0u);
+        mma_tf32(d, da_hi + adv, db_lo + adv, idesc, 1u);
+        mma_tf32(d, da_hi + adv, db_hi + adv, idesc, 1u);
+      }
+      umma_commit(sm.bar + buf);  // arrives when the MMAs above have finished (and released shared memory)
+    }
+    if (kb > 0) drain(tmem_base + (uint32_t)((buf ^ 1) * TN), warp, n_tile, acc);  // overlaps the MMAs just issued
+    mbar_wait(sm.bar + buf, parity[buf]);
+    parity[buf] ^= 1u;
+    tc_fence_after();
+  }
+  if (kb > 0) drain(tmem_base + (uint32_t)(((kb - 1) & 1) * TN), warp, n_tile, acc);
+}
+
+__device__ __forceinline__ uint32_t tmem_alloc(const Smem& sm, int warp) {
+  if (threadIdx.x == 0) {
+    mbar_init(sm.bar, 1);
+    mbar_init(sm.bar + 1, 1);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_slot)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *sm.tmem_slot;
+}
+__device__ __forceinline__ void tmem_free(uint32_t taddr, int warp) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(TMEM_COLS) : "memory");
+}
+
+// ---- LINEAR: grid (cols / 128, ceil(n_out_pad / 256)); 128 threads.
+// op fields as OP_LINEAR plus a10 = offset, a11 = leading dimension of the [out][in] copy of the weights.
+__global__ void __launch_bounds__(128)
+vg_linear_tc(vm::Op op, float* __restrict__ rows, int C, const float* __restrict__ par) {
+  extern __shared__ unsigned char smem_raw[];
+  const Smem sm = carve(smem_raw);
+  const int in_row = op.a[0], n_in = op.a[1], out_row = op.a[4], n_out = op.a[5], b_off = op.a[6], act = op.a[7],
+            accumulate = op.a[8], pre_row = op.a[9], tw_off = op.a[10], tw_ld = op.a[11], n_real = op.a[12];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
+  const int n_valid = min(TN, n_out - j0);                    // padded outputs this tile writes
+  const int n_rows_b = max(0, min(TN, n_real - j0));          // rows of the [out][in] weight copy that exist
+  const int n_tile = (n_valid + 15) & ~15;
+  const uint32_t tmem_d = tmem_alloc(sm, warp);
+  const float* a_src = rows + (size_t)in_row * C + s0;        // [i][s]
+  const float* b_src = par + tw_off + (size_t)j0 * tw_ld;      // [j][i]
+  float acc[TN];
+  k_loop(sm, tmem_d, n_tile, n_in, warp,
+         [&](int k0, int kv) { stage_transposed(sm.a_hi, sm.a_lo, a_src + (size_t)k0 * C, (size_t)C, kv, tid, 128); },
+         [&](int k0, int kv) { stage_kmajor(sm.b_hi, sm.b_lo, b_src + k0, (size_t)tw_ld, n_tile, n_rows_b, kv, tid, 128, -1, nullptr); },
+         acc);
+  // epilogue: this thread holds sample s0 + 32 warp + lane (its TMEM lane); acc[c] = output j0 + c
+  const size_t col = (size_t)s0 + 32 * warp + lane;
+  const int acc_row = pre_row >= 0 ? pre_row : out_row;
+#pragma unroll
+  for (int c = 0; c < TN; ++c) {
+    const int j = j0 + c;
+    if (c < n_valid) {
+      float x = acc[c] + (b_off >= 0 ? __ldg(par + b_off + j) : 0.0f);
+      if (accumulate) x += rows[(size_t)(acc_row + j) * C + col];
+      if (pre_row >= 0) rows[(size_t)(pre_row + j) * C + col] = x;
+      rows[(size_t)(out_row + j) * C + col] = vm::act_fwd(act, x);
+    }
+  }
+  tmem_free(tmem_d, warp);
+}
+
+// ---- LINEAR_DW: grid (ceil(NA / 128), ceil(n_out / 256), slabs); 128 threads; K = samples of the slab.
+__global__ void __launch_bounds__(128)
+vg_dw_tc(vm::Op op, const float* __restrict__ rows, int C, int cols, int slab, float* __restrict__ grad) {
+  extern __shared__ unsigned char smem_raw[];
+  const Smem sm = carve(smem_raw);
+  const int in_row = op.a[0], n_in = op.a[1], g_row = op.a[2], n_out = op.a[3], w_off = op.a[4], ld = op.a[5],
+            b_off = op.a[6];
+  const int NA = n_in + (b_off >= 0 ? 1 : 0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
+  const int s_begin = blockIdx.z * slab, s_end = min(cols, s_begin + slab);
+  const int m_valid = min(TM, NA - i0), n_valid = min(TN, n_out - j0);
+  const int n_tile = (n_valid + 15) & ~15;
+  const uint32_t tmem_d = tmem_alloc(sm, warp);
+  const float* a_src = rows + (size_t)(in_row + i0) * C + s_begin;
+  const float* b_src = rows + (size_t)(g_row + j0) * C + s_begin;
+  const int ones_r = (b_off >= 0 && n_in - i0 >= 0 && n_in - i0 < TM) ? n_in - i0 : -1;  // tile row of the ones row
+  const float* ones_src = rows + s_begin;  // row 0 of the workspace is the constant-ones row (vm_ops.cuh ROW_ONES)
+  float acc[TN];
+  k_loop(sm, tmem_d, n_tile, s_end - s_begin, warp,
+         [&](int k0, int kv) { stage_kmajor(sm.a_hi, sm.a_lo, a_src + k0, (size_t)C, TM, m_valid, kv, tid, 128, ones_r, ones_src + k0); },
+         [&](int k0, int kv) { stage_kmajor(sm.b_hi, sm.b_lo, b_src + k0, (size_t)C, n_tile, n_valid, kv, tid, 128, -1, nullptr); },
+         acc);
+  const int i = i0 + 32 * warp + lane;  // TMEM lane = input index
+  if (i < NA) {
+    float* dst = grad + (i < n_in ? w_off + (size_t)i * ld : (size_t)b_off) + j0;
+#pragma unroll
+    for (int c = 0; c < TN; ++c)
+      if (c < n_valid) atomicAdd(dst + c, acc[c]);
+  }
+  tmem_free(tmem_d, warp);
+}
+
+}  // namespace vmtc
