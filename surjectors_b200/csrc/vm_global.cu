@@ -313,7 +313,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, bool backward, int with_base, cons
       if (op.code == vm::OP_LINEAR) {
         if (use_tc && use_tc_lin && op.a[1] >= 32 && op.a[5] >= 32) {  // tcgen05 3xTF32 tiles for real contractions
           dim3 grid(cols / vmtc::TM, (op.a[5] + vmtc::TN - 1) / vmtc::TN);
-          vmtc::vg_linear_tc<<<grid, 128, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, k.par);
+          vmtc::vg_linear_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, k.par);
         } else {
           dim3 grid(cols / vm::LBM, (op.a[5] + vm::LBN - 1) / vm::LBN);
           vm::vg_linear<<<grid, 256, 0, st>>>(op, k.rows, C, k.par);
@@ -322,9 +322,12 @@ int vm_global_run(VmPlan* v, cudaStream_t st, bool backward, int with_base, cons
       } else if (op.code == vm::OP_LINEAR_DW) {
         const int NA = op.a[1] + (op.a[6] >= 0 ? 1 : 0), NG = op.a[3];
         if (use_tc && use_tc_dw && NA >= 32 && NG >= 32) {
-          const int slab = 4096;
+          // sample slabs sized so the grid fills the machine about twice (2 CTAs per SM x 148 SMs x 2)
+          const int tiles = ((NA + vmtc::TM - 1) / vmtc::TM) * ((NG + vmtc::TN - 1) / vmtc::TN);
+          const int want = std::max(1, (592 + tiles - 1) / tiles);
+          const int slab = std::max(512, (cols / want) / 128 * 128);
           dim3 grid((NA + vmtc::TM - 1) / vmtc::TM, (NG + vmtc::TN - 1) / vmtc::TN, (cols + slab - 1) / slab);
-          vmtc::vg_dw_tc<<<grid, 128, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, cols, slab, k.grad);
+          vmtc::vg_dw_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, cols, slab, k.grad);
         } else {
           const int slab = 2048;
           dim3 grid((NA + vm::DBI - 1) / vm::DBI, (NG + vm::DBJ - 1) / vm::DBJ, (cols + slab - 1) / slab);

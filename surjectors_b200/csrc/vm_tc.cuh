@@ -122,6 +122,9 @@ __device__ __forceinline__ Smem carve(unsigned char* raw) {
   return s;
 }
 
+constexpr int NTHR = 256;    // 8 warps: all stage operands; warps w and w + 4 share TMEM lanes 32 (w % 4) and split the columns
+constexpr int NCOL = TN / 2;  // accumulator columns per thread
+
 // split-store 4 consecutive-k values of row r into the hi / lo tiles (one 16-byte core-matrix row each)
 __device__ __forceinline__ void put4(float* hi, float* lo, int r, int k, float4 v) {
   float4 h, l;
@@ -132,78 +135,114 @@ __device__ __forceinline__ void put4(float* hi, float* lo, int r, int k, float4 
   *reinterpret_cast<float4*>(lo + o) = l;
 }
 
-// Operand whose source is K-major: src[(row0 + r) * pitch + k0 + k], r < n_rows (of `tile_rows`), k < 32.
-// Rows >= n_valid_rows and k >= k_valid are zero.  `special_row`/`special_src`: one row may come from
-// another base pointer (the ones row that carries the bias gradient).
-__device__ __forceinline__ void stage_kmajor(float* hi, float* lo, const float* __restrict__ src, size_t pitch,
-                                             int tile_rows, int n_valid_rows, int k_valid, int tid, int nthreads,
-                                             int special_row, const float* __restrict__ special_src) {
-  for (int idx = tid; idx < tile_rows * 8; idx += nthreads) {
-    const int r = idx >> 3, c4 = idx & 7;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < n_valid_rows) {
-      const float* p = (r == special_row ? special_src : src + (size_t)r * pitch) + 4 * c4;
-      if (4 * c4 + 3 < k_valid) v = *reinterpret_cast<const float4*>(p);
-      else {
-        if (4 * c4 + 0 < k_valid) v.x = p[0];
-        if (4 * c4 + 1 < k_valid) v.y = p[1];
-        if (4 * c4 + 2 < k_valid) v.z = p[2];
-      }
-    }
-    put4(hi, lo, r, 4 * c4, v);
-  }
-}
-
-// Operand whose source is MN-major: src[(k0 + k) * pitch + row0 + r] (rows contiguous), 128 rows x 32 k.
-__device__ __forceinline__ void stage_transposed(float* hi, float* lo, const float* __restrict__ src, size_t pitch,
-                                                 int k_valid, int tid, int nthreads) {
-  // thread -> (row r = idx % 128, k group of 4 = idx / 128): coalesced along rows for every k
-  for (int idx = tid; idx < TM * 8; idx += nthreads) {
-    const int r = idx & (TM - 1), c4 = idx >> 7;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* p = src + (size_t)(4 * c4) * pitch + r;
-    if (4 * c4 + 0 < k_valid) v.x = p[0];
-    if (4 * c4 + 1 < k_valid) v.y = p[pitch];
-    if (4 * c4 + 2 < k_valid) v.z = p[2 * pitch];
-    if (4 * c4 + 3 < k_valid) v.w = p[3 * pitch];
-    put4(hi, lo, r, 4 * c4, v);
-  }
-}
-
-// acc[c] += TMEM buffer (this warp's 32 lanes, columns [0, n_tile))
-__device__ __forceinline__ void drain(uint32_t tmem_buf, int warp, int n_tile, float (&acc)[TN]) {
+// Operand loaders: `load` issues the global loads of one K block into registers (so their latency
+// hides behind the MMAs of the previous block), `store` splits and writes them to shared memory.
+// K-major source: src[r * pitch + k], rows r < n_valid_rows of a tile of tile_rows (<= 128) rows.  One
+// row may come from another pointer (the ones row that carries the bias gradient).  A warp's 32
+// loads cover 8 rows x 64 contiguous bytes; its 8-lane store phases are 128 contiguous bytes.
+struct LoadKMajor {
+  const float* src; size_t pitch; int tile_rows, n_valid_rows, special_row; const float* special_src;
+  float4 v[4];
+  __device__ __forceinline__ void load(int k0, int k_valid, int tid) {
 #pragma unroll
-  for (int c0 = 0; c0 < TN; c0 += 32) {
-    if (c0 < n_tile) {
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * NTHR;
+      const int r = (idx & 7) + 8 * (idx >> 6), c4 = (idx >> 3) & 7;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < n_valid_rows) {
+        const float* p = (r == special_row ? special_src : src + (size_t)r * pitch) + k0 + 4 * c4;
+        if (4 * c4 + 3 < k_valid) t = *reinterpret_cast<const float4*>(p);
+        else {
+          if (4 * c4 + 0 < k_valid) t.x = p[0];
+          if (4 * c4 + 1 < k_valid) t.y = p[1];
+          if (4 * c4 + 2 < k_valid) t.z = p[2];
+        }
+      }
+      v[it] = t;
+    }
+  }
+  __device__ __forceinline__ void store(float* hi, float* lo, int tid) const {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * NTHR;
+      const int r = (idx & 7) + 8 * (idx >> 6), c4 = (idx >> 3) & 7;
+      if (r < tile_rows) put4(hi, lo, r, 4 * c4, v[it]);
+    }
+  }
+};
+
+// MN-major source: src[k * pitch + r] (rows contiguous), 128 rows x 32 k: coalesced along rows for every k.
+struct LoadTransposed {
+  const float* src; size_t pitch;
+  float4 v[4];
+  __device__ __forceinline__ void load(int k0, int k_valid, int tid) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * NTHR;
+      const int r = idx & (TM - 1), c4 = idx >> 7;
+      const float* p = src + (size_t)(k0 + 4 * c4) * pitch + r;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * c4 + 0 < k_valid) t.x = p[0];
+      if (4 * c4 + 1 < k_valid) t.y = p[pitch];
+      if (4 * c4 + 2 < k_valid) t.z = p[2 * pitch];
+      if (4 * c4 + 3 < k_valid) t.w = p[3 * pitch];
+      v[it] = t;
+    }
+  }
+  __device__ __forceinline__ void store(float* hi, float* lo, int tid) const {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * NTHR;
+      put4(hi, lo, idx & (TM - 1), 4 * (idx >> 7), v[it]);
+    }
+  }
+};
+
+// acc[c] += TMEM buffer: this warp's 32 lanes, columns [col0, col0 + NCOL) clipped to n_tile
+__device__ __forceinline__ void drain(uint32_t tmem_buf, int lane_base, int col0, int n_tile, float (&acc)[NCOL]) {
+#pragma unroll
+  for (int c0 = 0; c0 < NCOL; c0 += 32) {
+    if (col0 + c0 < n_tile) {
       float v[32];
-      tmem_ld32(tmem_buf + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, v);
+      tmem_ld32(tmem_buf + ((uint32_t)lane_base << 16) + (uint32_t)(col0 + c0), v);
 #pragma unroll
       for (int q = 0; q < 32; ++q) acc[c0 + q] += v[q];
     }
   }
 }
 
-// K loop shared by both kernels.  Per K block: stage operands (hi / lo split) -> 12 MMAs into TMEM
-// buffer kb & 1 (fresh accumulator) -> commit; the previous block's buffer is drained into `acc`
-// while those MMAs run.  On return `acc` holds this thread's row (TMEM lane) of D.
-template <class StageA, class StageB>
-__device__ __forceinline__ void k_loop(const Smem& sm, uint32_t tmem_base, int n_tile, int K, int warp, StageA stage_a,
-                                       StageB stage_b, float (&acc)[TN]) {
+// K loop shared by both kernels.  Per K block: (wait for the previous block's MMAs) -> split-store
+// the prefetched operands -> 12 MMAs into TMEM buffer kb & 1 (fresh accumulator) -> commit -> prefetch
+// the next block's operands into registers and drain the previous block's buffer into `acc`, both
+// while the MMAs run.  On return `acc` holds columns [col0, col0 + NCOL) of this thread's row of D.
+template <class LA, class LB>
+__device__ __forceinline__ void k_loop(const Smem& sm, uint32_t tmem_base, int n_tile, int K, int lane_base, int col0,
+                                       LA& la, LB& lb, float (&acc)[NCOL]) {
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   const uint64_t da_hi = make_desc(smem_u32(sm.a_hi)), da_lo = make_desc(smem_u32(sm.a_lo));
   const uint64_t db_hi = make_desc(smem_u32(sm.b_hi)), db_lo = make_desc(smem_u32(sm.b_lo));
+  const int tid = threadIdx.x;
 #pragma unroll
-  for (int c = 0; c < TN; ++c) acc[c] = 0.0f;
+  for (int c = 0; c < NCOL; ++c) acc[c] = 0.0f;
   uint32_t parity[2] = {0u, 0u};
-  int kb = 0;
-  for (int k0 = 0; k0 < K; k0 += BK, ++kb) {
+  const int nkb = (K + BK - 1) / BK;
+  if (nkb > 0) {
+    la.load(0, min(BK, K), tid);
+    lb.load(0, min(BK, K), tid);
+  }
+  for (int kb = 0; kb < nkb; ++kb) {
     const int buf = kb & 1;
-    stage_a(k0, min(BK, K - k0));
-    stage_b(k0, min(BK, K - k0));
+    if (kb > 0) {  // MMAs of block kb - 1 done: shared memory is free, TMEM buffer buf ^ 1 is complete
+      mbar_wait(sm.bar + (buf ^ 1), parity[buf ^ 1]);
+      parity[buf ^ 1] ^= 1u;
+      tc_fence_after();
+    }
+    la.store(sm.a_hi, sm.a_lo, tid);
+    lb.store(sm.b_hi, sm.b_lo, tid);
     fence_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
     tc_fence_before();    // orders the tcgen05.ld of the previous drain before the MMAs that reuse that buffer
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(buf * TN);
 #pragma unroll
@@ -215,12 +254,19 @@ __device__ __forceinline__ void k_loop(const Smem& sm, uint32_t tmem_base, int n
       }
       umma_commit(sm.bar + buf);  // arrives when the MMAs above have finished (and released shared memory)
     }
-    if (kb > 0) drain(tmem_base + (uint32_t)((buf ^ 1) * TN), warp, n_tile, acc);  // overlaps the MMAs just issued
-    mbar_wait(sm.bar + buf, parity[buf]);
-    parity[buf] ^= 1u;
-    tc_fence_after();
+    if (kb + 1 < nkb) {
+      const int k1 = (kb + 1) * BK;
+      la.load(k1, min(BK, K - k1), tid);
+      lb.load(k1, min(BK, K - k1), tid);
+    }
+    if (kb > 0) drain(tmem_base + (uint32_t)((buf ^ 1) * TN), lane_base, col0, n_tile, acc);
   }
-  if (kb > 0) drain(tmem_base + (uint32_t)(((kb - 1) & 1) * TN), warp, n_tile, acc);
+  if (nkb > 0) {
+    const int buf = (nkb - 1) & 1;
+    mbar_wait(sm.bar + buf, parity[buf]);
+    tc_fence_after();
+    drain(tmem_base + (uint32_t)(buf * TN), lane_base, col0, n_tile, acc);
+  }
 }
 
 __device__ __forceinline__ uint32_t tmem_alloc(const Smem& sm, int warp) {
@@ -246,9 +292,10 @@ __device__ __forceinline__ void tmem_free(uint32_t taddr, int warp) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(TMEM_COLS) : "memory");
 }
 
-// ---- LINEAR: grid (cols / 128, ceil(n_out_pad / 256)); 128 threads.
-// op fields as OP_LINEAR plus a10 = offset, a11 = leading dimension of the [out][in] copy of the weights.
-__global__ void __launch_bounds__(128)
+// ---- LINEAR: grid (cols / 128, ceil(n_out_pad / 128)); 256 threads.
+// op fields as OP_LINEAR plus a10 / a11 = offset / leading dimension of the [out][in] copy of the weights,
+// a12 = number of real (unpadded) outputs.
+__global__ void __launch_bounds__(NTHR, 2)
 vg_linear_tc(vm::Op op, float* __restrict__ rows, int C, const float* __restrict__ par) {
   extern __shared__ unsigned char smem_raw[];
   const Smem sm = carve(smem_raw);
@@ -260,20 +307,18 @@ vg_linear_tc(vm::Op op, float* __restrict__ rows, int C, const float* __restrict
   const int n_rows_b = max(0, min(TN, n_real - j0));          // rows of the [out][in] weight copy that exist
   const int n_tile = (n_valid + 15) & ~15;
   const uint32_t tmem_d = tmem_alloc(sm, warp);
-  const float* a_src = rows + (size_t)in_row * C + s0;        // [i][s]
-  const float* b_src = par + tw_off + (size_t)j0 * tw_ld;      // [j][i]
-  float acc[TN];
-  k_loop(sm, tmem_d, n_tile, n_in, warp,
-         [&](int k0, int kv) { stage_transposed(sm.a_hi, sm.a_lo, a_src + (size_t)k0 * C, (size_t)C, kv, tid, 128); },
-         [&](int k0, int kv) { stage_kmajor(sm.b_hi, sm.b_lo, b_src + k0, (size_t)tw_ld, n_tile, n_rows_b, kv, tid, 128, -1, nullptr); },
-         acc);
-  // epilogue: this thread holds sample s0 + 32 warp + lane (its TMEM lane); acc[c] = output j0 + c
-  const size_t col = (size_t)s0 + 32 * warp + lane;
+  LoadTransposed la{rows + (size_t)in_row * C + s0, (size_t)C};                                   // A[s][i] from in[i][s]
+  LoadKMajor lb{par + tw_off + (size_t)j0 * tw_ld, (size_t)tw_ld, n_tile, n_rows_b, -1, nullptr};  // B[j][i]
+  const int lane_base = 32 * (warp & 3), col0 = NCOL * (warp >> 2);
+  float acc[NCOL];
+  k_loop(sm, tmem_d, n_tile, n_in, lane_base, col0, la, lb, acc);
+  // epilogue: this thread holds sample s0 + lane_base + lane (its TMEM lane); acc[c] = output j0 + col0 + c
+  const size_t col = (size_t)s0 + lane_base + lane;
   const int acc_row = pre_row >= 0 ? pre_row : out_row;
 #pragma unroll
-  for (int c = 0; c < TN; ++c) {
-    const int j = j0 + c;
-    if (c < n_valid) {
+  for (int c = 0; c < NCOL; ++c) {
+    const int j = j0 + col0 + c;
+    if (col0 + c < n_valid) {
       float x = acc[c] + (b_off >= 0 ? __ldg(par + b_off + j) : 0.0f);
       if (accumulate) x += rows[(size_t)(acc_row + j) * C + col];
       if (pre_row >= 0) rows[(size_t)(pre_row + j) * C + col] = x;
@@ -283,8 +328,8 @@ vg_linear_tc(vm::Op op, float* __restrict__ rows, int C, const float* __restrict
   tmem_free(tmem_d, warp);
 }
 
-// ---- LINEAR_DW: grid (ceil(NA / 128), ceil(n_out / 256), slabs); 128 threads; K = samples of the slab.
-__global__ void __launch_bounds__(128)
+// ---- LINEAR_DW: grid (ceil(NA / 128), ceil(n_out / 128), slabs); 256 threads; K = samples of the slab.
+__global__ void __launch_bounds__(NTHR, 2)
 vg_dw_tc(vm::Op op, const float* __restrict__ rows, int C, int cols, int slab, float* __restrict__ grad) {
   extern __shared__ unsigned char smem_raw[];
   const Smem sm = carve(smem_raw);
@@ -297,21 +342,19 @@ vg_dw_tc(vm::Op op, const float* __restrict__ rows, int C, int cols, int slab, f
   const int m_valid = min(TM, NA - i0), n_valid = min(TN, n_out - j0);
   const int n_tile = (n_valid + 15) & ~15;
   const uint32_t tmem_d = tmem_alloc(sm, warp);
-  const float* a_src = rows + (size_t)(in_row + i0) * C + s_begin;
-  const float* b_src = rows + (size_t)(g_row + j0) * C + s_begin;
   const int ones_r = (b_off >= 0 && n_in - i0 >= 0 && n_in - i0 < TM) ? n_in - i0 : -1;  // tile row of the ones row
-  const float* ones_src = rows + s_begin;  // row 0 of the workspace is the constant-ones row (vm_ops.cuh ROW_ONES)
-  float acc[TN];
-  k_loop(sm, tmem_d, n_tile, s_end - s_begin, warp,
-         [&](int k0, int kv) { stage_kmajor(sm.a_hi, sm.a_lo, a_src + k0, (size_t)C, TM, m_valid, kv, tid, 128, ones_r, ones_src + k0); },
-         [&](int k0, int kv) { stage_kmajor(sm.b_hi, sm.b_lo, b_src + k0, (size_t)C, n_tile, n_valid, kv, tid, 128, -1, nullptr); },
-         acc);
-  const int i = i0 + 32 * warp + lane;  // TMEM lane = input index
+  // row 0 of the workspace is the constant-ones row (vm_ops.cuh ROW_ONES)
+  LoadKMajor la{rows + (size_t)(in_row + i0) * C + s_begin, (size_t)C, TM, m_valid, ones_r, rows + s_begin};
+  LoadKMajor lb{rows + (size_t)(g_row + j0) * C + s_begin, (size_t)C, n_tile, n_valid, -1, nullptr};
+  const int lane_base = 32 * (warp & 3), col0 = NCOL * (warp >> 2);
+  float acc[NCOL];
+  k_loop(sm, tmem_d, n_tile, s_end - s_begin, lane_base, col0, la, lb, acc);
+  const int i = i0 + lane_base + lane;  // TMEM lane = input index
   if (i < NA) {
-    float* dst = grad + (i < n_in ? w_off + (size_t)i * ld : (size_t)b_off) + j0;
+    float* dst = grad + (i < n_in ? w_off + (size_t)i * ld : (size_t)b_off) + j0 + col0;
 #pragma unroll
-    for (int c = 0; c < TN; ++c)
-      if (c < n_valid) atomicAdd(dst + c, acc[c]);
+    for (int c = 0; c < NCOL; ++c)
+      if (col0 + c < n_valid) atomicAdd(dst + c, acc[c]);
   }
   tmem_free(tmem_d, warp);
 }
