@@ -233,8 +233,11 @@ __device__ __forceinline__ void k_loop(const Smem& sm, uint32_t tmem_base, int n
   for (int kb = 0; kb < nkb; ++kb) {
     const int buf = kb & 1;
     if (kb > 0) {  // MMAs of block kb - 1 done: shared memory is free, TMEM buffer buf ^ 1 is complete
-      mbar_wait(sm.bar + (buf ^ 1), parity[buf ^ 1]);
+      // one warp polls the mbarrier, the others sleep in the hardware barrier (8 polling warps were
+      // measured to spend 2/3 of the kernel's issue slots on the try_wait loop)
+      if (tid < 32) mbar_wait(sm.bar + (buf ^ 1), parity[buf ^ 1]);
       parity[buf ^ 1] ^= 1u;
+      __syncthreads();
       tc_fence_after();
     }
     la.store(sm.a_hi, sm.a_lo, tid);
@@ -263,7 +266,8 @@ __device__ __forceinline__ void k_loop(const Smem& sm, uint32_t tmem_base, int n
   }
   if (nkb > 0) {
     const int buf = (nkb - 1) & 1;
-    mbar_wait(sm.bar + buf, parity[buf]);
+    if (tid < 32) mbar_wait(sm.bar + buf, parity[buf]);
+    __syncthreads();
     tc_fence_after();
     drain(tmem_base + (uint32_t)(buf * TN), lane_base, col0, n_tile, acc);
   }
