@@ -352,6 +352,13 @@ def run_b200(args):
   except Exception:  # noqa: BLE001
     pass
   hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+  traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of the kernel, from the committed ncu --set full capture
+  try:
+    t = json.load(open(os.path.join(ROOT, "profiles", "r1_cfg2_bwd_traffic.json")))
+    if args.config == "cfg2" and B == BATCH:
+      traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+  except Exception:  # noqa: BLE001
+    pass
   ach_tf = flops_launch / (bwd_pair_ms * 1e-3) / 1e12
   ach_gb = bytes_launch / (bwd_pair_ms * 1e-3) / 1e9
   roofline = {
@@ -359,7 +366,7 @@ def run_b200(args):
     "bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
     "peak_source": "measured here with surj_bench_fp32_peak (FFMA probe); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
     "flops_per_launch": flops_launch, "flops_dense_as_reference_per_launch": 3.0 * dense * B,
-    "us_per_launch": 1e3 * bwd_pair_ms, "traffic": None,
+    "us_per_launch": 1e3 * bwd_pair_ms, "traffic": traffic,
     "hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
             "bytes_per_launch": bytes_launch,
             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"},
