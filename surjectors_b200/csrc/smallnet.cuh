@@ -370,6 +370,36 @@ SURJ_DEV void mlp_bwd(const float* __restrict__ sp, const float (&in)[M::IN], co
   lin_bwd_in<L, false>(sp, g_pre, g_in);
 }
 
+// Forward through the MLP keeping every layer's pre-activations alive on the recursion stack, then
+// `gfun(out, g_out)` turns the network output into its cotangent, then backward.  One forward
+// instead of the two that mlp_fwd + mlp_bwd spend (shorter instruction stream: the generated
+// kernels are instruction-fetch bound).
+template <class M, class Sink, class G>
+SURJ_DEV void mlp_fwd_bwd(const float* __restrict__ sp, const float (&in)[M::IN], G& gfun, float (&g_in)[M::IN],
+                          Sink& sink) {
+  using L = typename M::First;
+  float pre[L::OUT];
+  lin_pre<L>(sp, in, pre);
+  float g_pre[L::OUT];
+  if constexpr (M::N == 1) {
+    float out[L::OUT], g_out[L::OUT];
+#pragma unroll
+    for (int j = 0; j < L::OUT; ++j) out[j] = act_fwd<L::ACT>(pre[j]);
+    gfun(out, g_out);
+#pragma unroll
+    for (int j = 0; j < L::OUT; ++j) g_pre[j] = act_bwd<L::ACT>(pre[j], g_out[j]);
+  } else {
+    float h[L::OUT], g_h[L::OUT];
+#pragma unroll
+    for (int j = 0; j < L::OUT; ++j) h[j] = act_fwd<L::ACT>(pre[j]);
+    mlp_fwd_bwd<typename M::Rest, Sink, G>(sp, h, gfun, g_h, sink);
+#pragma unroll
+    for (int j = 0; j < L::OUT; ++j) g_pre[j] = act_bwd<L::ACT>(pre[j], g_h[j]);
+  }
+  sink.template linear<L>(in, g_pre);
+  lin_bwd_in<L, false>(sp, g_pre, g_in);
+}
+
 // -------------------------------------------------------------------------- MADE
 // First masked layer takes y (masked weights) plus an optional dense context Linear on c;
 // the remaining masked layers are an Mlp whose Lin predicates carry the MADE masks.
@@ -424,6 +454,34 @@ SURJ_DEV void made_bwd(const float* __restrict__ sp, const float (&y)[MD::D], co
 #pragma unroll
   for (int j = 0; j < L0::OUT; ++j) h[j] = act_fwd<L0::ACT>(pre[j]);
   mlp_bwd<typename MD::REST, Sink>(sp, h, g_out, g_h, sink);
+#pragma unroll
+  for (int j = 0; j < L0::OUT; ++j) g_pre[j] = act_bwd<L0::ACT>(pre[j], g_h[j]);
+  sink.template linear<L0>(y, g_pre);
+  lin_bwd_in<L0, false>(sp, g_pre, g_y);
+  if constexpr (DC > 0) {
+    using C = typename MD::CTX;
+    sink.template linear<C>(c, g_pre);
+    lin_bwd_in<C, false>(sp, g_pre, g_c);
+  }
+}
+
+template <class MD, int DC, class Sink, class G>
+SURJ_DEV void made_fwd_bwd(const float* __restrict__ sp, const float (&y)[MD::D], const float (&c)[DC > 0 ? DC : 1],
+                           G& gfun, float (&g_y)[MD::D], float (&g_c)[DC > 0 ? DC : 1], Sink& sink) {
+  using L0 = typename MD::L0;
+  float pre[L0::OUT];
+  lin_pre<L0>(sp, y, pre);
+  if constexpr (DC > 0) {
+    using C = typename MD::CTX;
+    float cp[C::OUT];
+    lin_pre<C>(sp, c, cp);
+#pragma unroll
+    for (int j = 0; j < L0::OUT; ++j) pre[j] += cp[j];
+  }
+  float h[L0::OUT], g_h[L0::OUT], g_pre[L0::OUT];
+#pragma unroll
+  for (int j = 0; j < L0::OUT; ++j) h[j] = act_fwd<L0::ACT>(pre[j]);
+  mlp_fwd_bwd<typename MD::REST, Sink, G>(sp, h, gfun, g_h, sink);
 #pragma unroll
   for (int j = 0; j < L0::OUT; ++j) g_pre[j] = act_bwd<L0::ACT>(pre[j], g_h[j]);
   sink.template linear<L0>(y, g_pre);
@@ -551,19 +609,20 @@ struct Coupling {
   SURJ_DEV static void backward(const float* __restrict__ sp, const float*, const float (&in)[D],
                                 const float (&x)[XArr<DX>::n], const float (&g_out)[D], float g_lc, float (&g_in)[D],
                                 float (&g_x)[XArr<DX>::n], Sink& sink) {
-    float m[CIN], th[2 * D], g_th[2 * D], g_m[CIN];
+    float m[CIN], g_m[CIN];
     cond_in(in, x, m);
-    mlp_fwd<COND>(sp, m, th);
+    auto gfun = [&](const float (&th)[2 * D], float (&g_th)[2 * D]) {
 #pragma unroll
-    for (int j = 0; j < 2 * D; ++j) g_th[j] = 0.0f;
+      for (int j = 0; j < 2 * D; ++j) g_th[j] = 0.0f;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      if (pass(d)) g_in[d] = g_out[d];
-      else
-        affine_inv_bwd<INNER>(in[d], th[TI::shift(d)], th[TI::lscale(d)], g_out[d], g_lc, g_in[d],
-                              g_th[TI::shift(d)], g_th[TI::lscale(d)]);
-    }
-    mlp_bwd<COND, Sink>(sp, m, g_th, g_m, sink);
+      for (int d = 0; d < D; ++d) {
+        if (pass(d)) g_in[d] = g_out[d];
+        else
+          affine_inv_bwd<INNER>(in[d], th[TI::shift(d)], th[TI::lscale(d)], g_out[d], g_lc, g_in[d],
+                                g_th[TI::shift(d)], g_th[TI::lscale(d)]);
+      }
+    };
+    mlp_fwd_bwd<COND, Sink>(sp, m, gfun, g_m, sink);
 #pragma unroll
     for (int d = 0; d < D; ++d)
       if (pass(d)) g_in[d] += g_m[d];
@@ -600,11 +659,10 @@ struct DecoderTail {
   SURJ_DEV static void bwd(const float* __restrict__ sp, const float (&z)[K], const float (&x)[XArr<DX>::n],
                            const float (&v)[NV], float g, float (&g_z)[K], float (&g_v)[NV],
                            float (&g_x)[XArr<DX>::n], Sink& sink) {
-    float c[CIN], th[2 * NV], g_th[2 * NV], g_c[CIN];
+    float c[CIN], g_c[CIN];
     cat(z, x, c);
-    mlp_fwd<DEC>(sp, c, th);
-    normal_lp_bwd<NV>(v, th, g, g_th, g_v);
-    mlp_bwd<DEC, Sink>(sp, c, g_th, g_c, sink);
+    auto gfun = [&](const float (&th)[2 * NV], float (&g_th)[2 * NV]) { normal_lp_bwd<NV>(v, th, g, g_th, g_v); };
+    mlp_fwd_bwd<DEC, Sink>(sp, c, gfun, g_c, sink);
 #pragma unroll
     for (int d = 0; d < K; ++d) g_z[d] += g_c[d];
     if constexpr (USEX) {
@@ -671,21 +729,35 @@ struct CouplingFunnel {
   SURJ_DEV static void backward(const float* __restrict__ sp, const float* scr, const float (&in)[D],
                                 const float (&x)[XArr<DX>::n], const float (&g_out)[K], float g_lc, float (&g_in)[D],
                                 float (&g_x)[XArr<DX>::n], Sink& sink) {
-    float faux[D], z[K], v[D - K], g_faux[D], g_z[K], g_v[D - K];
-    float lc_unused = 0.0f;
-    Cpl::inverse(sp, scr, in, x, faux, lc_unused);
-#pragma unroll
-    for (int d = 0; d < K; ++d) { z[d] = faux[d]; g_z[d] = g_out[d]; }
+    using TI = typename Cpl::TI;
+    float m[Cpl::CIN], g_m[Cpl::CIN], v[D - K], g_v[D - K];
+    Cpl::cond_in(in, x, m);
 #pragma unroll
     for (int j = 0; j < D - K; ++j) v[j] = in[K + j];
-    Tail::bwd(sp, z, x, v, g_lc, g_z, g_v, g_x, sink);
+    // one conditioner forward: theta -> z -> decoder forward + backward -> cotangent of theta
+    auto gfun = [&](const float (&th)[2 * D], float (&g_th)[2 * D]) {
+      float z[K], g_z[K];
 #pragma unroll
-    for (int d = 0; d < K; ++d) g_faux[d] = g_z[d];
+      for (int d = 0; d < K; ++d) {
+        float ld;
+        affine_inv<INNER>(in[d], th[TI::shift(d)], th[TI::lscale(d)], z[d], ld);
+        g_z[d] = g_out[d];
+      }
+      Tail::bwd(sp, z, x, v, g_lc, g_z, g_v, g_x, sink);
 #pragma unroll
-    for (int j = 0; j < D - K; ++j) g_faux[K + j] = 0.0f;  // faux[K:] is discarded by the funnel
-    Cpl::backward(sp, scr, in, x, g_faux, g_lc, g_in, g_x, sink);
+      for (int j = 0; j < 2 * D; ++j) g_th[j] = 0.0f;
 #pragma unroll
-    for (int j = 0; j < D - K; ++j) g_in[K + j] += g_v[j];
+      for (int d = 0; d < K; ++d)
+        affine_inv_bwd<INNER>(in[d], th[TI::shift(d)], th[TI::lscale(d)], g_z[d], g_lc, g_in[d], g_th[TI::shift(d)],
+                              g_th[TI::lscale(d)]);
+    };
+    mlp_fwd_bwd<COND, Sink>(sp, m, gfun, g_m, sink);
+#pragma unroll
+    for (int j = 0; j < D - K; ++j) g_in[K + j] = g_m[K + j] + g_v[j];  // dims >= K pass through and feed the conditioner
+    if constexpr (USEX) {
+#pragma unroll
+      for (int k = 0; k < DX; ++k) g_x[k] += g_m[D + k];
+    }
   }
 };
 
@@ -719,13 +791,14 @@ struct Maf {
   SURJ_DEV static void backward(const float* __restrict__ sp, const float*, const float (&in)[D],
                                 const float (&x)[XArr<DX>::n], const float (&g_out)[D], float g_lc, float (&g_in)[D],
                                 float (&g_x)[XArr<DX>::n], Sink& sink) {
-    float c[XArr<DC>::n], th[2 * D], g_th[2 * D], g_y[D], g_c[XArr<DC>::n];
+    float c[XArr<DC>::n], g_y[D], g_c[XArr<DC>::n];
     ctx(x, c);
-    made_fwd<MADE_, DC>(sp, in, c, th);
+    auto gfun = [&](const float (&th)[2 * D], float (&g_th)[2 * D]) {
 #pragma unroll
-    for (int d = 0; d < D; ++d)
-      affine_inv_bwd<INNER>(in[d], th[2 * d], th[2 * d + 1], g_out[d], g_lc, g_in[d], g_th[2 * d], g_th[2 * d + 1]);
-    made_bwd<MADE_, DC, Sink>(sp, in, c, g_th, g_y, g_c, sink);
+      for (int d = 0; d < D; ++d)
+        affine_inv_bwd<INNER>(in[d], th[2 * d], th[2 * d + 1], g_out[d], g_lc, g_in[d], g_th[2 * d], g_th[2 * d + 1]);
+    };
+    made_fwd_bwd<MADE_, DC, Sink>(sp, in, c, gfun, g_y, g_c, sink);
 #pragma unroll
     for (int d = 0; d < D; ++d) g_in[d] += g_y[d];
     if constexpr (DC > 0) {
@@ -773,21 +846,24 @@ struct MafFunnel {
   SURJ_DEV static void backward(const float* __restrict__ sp, const float*, const float (&in)[D],
                                 const float (&x)[XArr<DX>::n], const float (&g_out)[K], float g_lc, float (&g_in)[D],
                                 float (&g_x)[XArr<DX>::n], Sink& sink) {
-    float yp[K], v[D - K], c[DC], th[2 * K], z[K], g_z[K], g_v[D - K];
+    float yp[K], v[D - K], c[DC], g_v[D - K], g_yp[K], g_y2[K], g_c[DC];
     split(in, x, yp, v, c);
-    made_fwd<MADE_, DC>(sp, yp, c, th);
+    // one MADE forward: its output feeds the transform, the decoder runs forward + backward in the
+    // middle, and the cotangent of theta flows straight back
+    auto gfun = [&](const float (&th)[2 * K], float (&g_th)[2 * K]) {
+      float z[K], g_z[K];
 #pragma unroll
-    for (int d = 0; d < K; ++d) {
-      float ld;
-      affine_inv<INNER>(yp[d], th[2 * d], th[2 * d + 1], z[d], ld);
-      g_z[d] = g_out[d];
-    }
-    Tail::bwd(sp, z, x, v, g_lc, g_z, g_v, g_x, sink);
-    float g_th[2 * K], g_yp[K], g_y2[K], g_c[DC];
+      for (int d = 0; d < K; ++d) {
+        float ld;
+        affine_inv<INNER>(yp[d], th[2 * d], th[2 * d + 1], z[d], ld);
+        g_z[d] = g_out[d];
+      }
+      Tail::bwd(sp, z, x, v, g_lc, g_z, g_v, g_x, sink);
 #pragma unroll
-    for (int d = 0; d < K; ++d)
-      affine_inv_bwd<INNER>(yp[d], th[2 * d], th[2 * d + 1], g_z[d], g_lc, g_yp[d], g_th[2 * d], g_th[2 * d + 1]);
-    made_bwd<MADE_, DC, Sink>(sp, yp, c, g_th, g_y2, g_c, sink);
+      for (int d = 0; d < K; ++d)
+        affine_inv_bwd<INNER>(yp[d], th[2 * d], th[2 * d + 1], g_z[d], g_lc, g_yp[d], g_th[2 * d], g_th[2 * d + 1]);
+    };
+    made_fwd_bwd<MADE_, DC, Sink>(sp, yp, c, gfun, g_y2, g_c, sink);
 #pragma unroll
     for (int d = 0; d < K; ++d) g_in[d] = g_yp[d] + g_y2[d];
 #pragma unroll
