@@ -164,6 +164,15 @@ int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, const float*
 int surj_adam_step(SurjStream stream, float* params, const float* grads, float* mu, float* nu, int32_t* count,
                    int64_t n, float lr, float b1, float b2, float eps, float grad_scale);
 
+/* --- sampling direction: Surjector.forward_and_likelihood_contribution through the chain in reverse
+ * (surjectors/_src/surjectors/chain.py:47-67): y_out[B, dim_in] and the summed forward log-det
+ * ld_out[B] for latents z[B, dim_out].  Implemented for chains of bijectors (MaskedCoupling,
+ * MaskedAutoregressive -- its D-pass recursion masked_autoregressive.py:63-71 --, Permutation); returns
+ * SURJ_E_UNSUPPORTED for LULinear (no forward upstream either, lu_linear.py:92-93) and for surjections. */
+int surj_chain_forward(const SurjPlan* plan, SurjStream stream, const float* z, const float* x, const float* params,
+                       float* y_out, float* ld_out, void* workspace, size_t workspace_bytes, int64_t batch);
+size_t surj_plan_forward_workspace_bytes(const SurjPlan* plan, int64_t batch);
+
 /* --- one training step = the jitted `step` of examples/coupling_inference_surjection.py:81-90:
  * loss = g_scale * sum(lp) (g_scale = -1: the examples' -sum; -1/B: the notebooks' -mean), its gradient
  * w.r.t. params (left in g_params) and the optax.adam update of params / mu / nu / count.  On the fused

@@ -53,10 +53,12 @@ class Surjector:
     return _runtime.run_transform(self, y, x, honour_x=True)
 
   def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):
-    raise NotImplementedError(
-      f"{type(self).__name__}: the sampling (forward) direction is outside the log_prob hot path built here "
-      "(SURVEY.md section 8f)"
-    )
+    """Sampling direction: implemented for chains of bijectors -- MaskedCoupling,
+    MaskedAutoregressive (the D-pass recursion of masked_autoregressive.py:63-71), Permutation; the C ABI
+    reports NotImplementedError for LULinear (no forward upstream, lu_linear.py:92-93) and surjections."""
+    from surjectors_b200 import _runtime
+
+    return _runtime.run_forward(self, z, x, honour_x=True)
 
   def _trace(self, d_in: int, dx: int):
     """-> list[LayerSpec], d_out"""
@@ -352,6 +354,18 @@ class AffineMaskedAutoregressiveInferenceFunnel(MaskedAutoregressiveInferenceFun
 
 
 # ----------------------------------------------------------------------- driver
+def input_dim_for_latent(transform, d_latent):
+  """Data-space width of a transform given its latent width (bijectors keep the width; a Chain of
+  bijectors too).  Dimension-reducing layers have no sampling direction here yet."""
+  layers = transform._transforms if isinstance(transform, Chain) else [transform]
+  for t in layers:
+    if isinstance(t, (Slice, MaskedCouplingInferenceFunnel, MaskedAutoregressiveInferenceFunnel)):
+      raise NotImplementedError(
+        f"{type(t).__name__}: sampling through dimension-reducing surjections (decoder sampling) is the next step "
+        "(SURVEY.md section 8f.1); log_prob and its gradient are implemented")
+  return d_latent
+
+
 def trace_chain(transform, d_in, dx, honour_x=True) -> ChainSpec:
   """Turn a transform into a ChainSpec inside the current hk frame."""
   fr = hk.current_frame()
@@ -389,7 +403,39 @@ class TransformedDistribution:
     return _runtime.run_transform(self.transform, y, x, honour_x=honour_x, base=self.base_distribution)
 
   def sample(self, sample_shape=(), x=None):
-    raise NotImplementedError("sampling is outside the log_prob hot path built here (SURVEY.md section 8f)")
+    """transformed_distribution.py:95-107."""
+    y, _ = self.sample_and_log_prob(sample_shape, x)
+    return y
 
   def sample_and_log_prob(self, sample_shape=(), x=None):
-    raise NotImplementedError("sampling is outside the log_prob hot path built here (SURVEY.md section 8f)")
+    """transformed_distribution.py:109-139: z ~ base, y = transform.forward(z), lp = lp_z - fldj.
+    Base draws use the haiku rng of `apply` (a NumPy generator here: JAX PRNG streams cannot be
+    reproduced, so parity of samples is distributional); the transform runs on the CUDA kernels."""
+    from surjectors_b200 import _runtime
+
+    if isinstance(sample_shape, int):
+      sample_shape = (sample_shape,)
+    sample_shape = tuple(sample_shape)
+    if x is not None and len(sample_shape) == 0:
+      sample_shape = (x.shape[0],)
+    if x is not None and sample_shape[0] != x.shape[0]:
+      raise AssertionError(f"[Chex] sample_shape {sample_shape} does not match the batch of x ({x.shape[0]})")
+    if len(sample_shape) != 1:
+      raise _sym.Unsupported("sample_shape must be (n,) (or () with a conditioning x)")
+    n = int(sample_shape[0])
+    loc = np.broadcast_arrays(np.asarray(getattr(getattr(self.base_distribution, "distribution", self.base_distribution), "loc", 0.0)))[0]
+    d = int(np.asarray(loc).shape[-1]) if np.asarray(loc).ndim else None
+    if d is None:
+      raise _sym.Unsupported("base distribution must have a vector event")
+    _sym.check_standard_normal_base(self.base_distribution, d)
+    fr = hk.current_frame()
+    device = x.device if x is not None else (fr.params.flat.device if hasattr(fr.params, "flat") else torch.device("cpu"))
+    rng = hk.next_rng_key()
+    if rng is None:
+      raise ValueError("sampling needs an rng: model.apply(params, rng, method='sample', ...)")
+    g = torch.Generator(device="cpu").manual_seed(int(rng.integers(0, 2**62)))
+    z = torch.randn((n, d), generator=g, dtype=torch.float32).to(device)
+    lp_z = (-0.5 * z * z - 0.9189385332046727).sum(-1)
+    honour_x = not isinstance(self.transform, MaskedCoupling)  # quirk Q1 applies to both directions
+    y, fldj = _runtime.run_forward(self.transform, z, x, honour_x=honour_x)
+    return y, lp_z - fldj

@@ -121,6 +121,32 @@ class Plan:
     return gp, gy, gx, lp
 
 
+def _plan_forward(self, z, x, flat):
+  """surj_chain_forward: (y, summed forward log-det) for latents z (sampling direction)."""
+  B = z.shape[0]
+  if not z.is_cuda:
+    raise _abi.SurjError("surjectors_b200 computes on CUDA tensors only (there is no CPU fallback)")
+  if z.dim() != 2 or z.shape[1] != self.dim_out or z.dtype != torch.float32 or not z.is_contiguous():
+    raise ValueError(f"z must be a contiguous float32 [B, {self.dim_out}] tensor, got {tuple(z.shape)} {z.dtype}")
+  y = torch.empty((B, self.dim_in), dtype=torch.float32, device=z.device)
+  ld = torch.empty(B, dtype=torch.float32, device=z.device)
+  if B == 0:
+    return y, ld
+  n = int(self._lib.surj_plan_forward_workspace_bytes(self._h, B))
+  key = ("gen", B, str(z.device))
+  ws = self._ws.get(key)
+  if ws is None or ws.numel() < n:
+    ws = torch.empty(max(n, 16), dtype=torch.uint8, device=z.device)
+    self._ws[key] = ws
+  st = self._lib.surj_chain_forward(self._h, _stream(z), z.data_ptr(), _ptr(x), flat.data_ptr(), y.data_ptr(),
+                                    ld.data_ptr(), ws.data_ptr(), n, B)
+  _abi.check(st, "surj_chain_forward")
+  return y, ld
+
+
+Plan.forward = _plan_forward
+
+
 def _plan_train_step(self, y, x, flat, g_scale, grads, opt, loss_out):
   """surj_train_step: fused log_prob+VJP kernel, gradient reduction with the Adam update in its last stage."""
   B = y.shape[0]
@@ -228,6 +254,31 @@ def run_transform(transform, y, x, honour_x=True, base=None):
   if torch.is_grad_enabled() and (flat.requires_grad or y.requires_grad or (xx is not None and xx.requires_grad)):
     return _LogProbFn.apply(plan, y, xx, flat)
   return plan.fwd(y, xx, flat, want_z=True)
+
+
+def run_forward(transform, z, x, honour_x=True):
+  """Sampling direction: trace `transform` (its structure is direction-independent) and run
+  forward_and_likelihood_contribution: returns (y, forward log-det)."""
+  from surjectors_b200 import _layers
+
+  fr = hk.current_frame()
+  z = _prep(z, "z")
+  x = _prep(x, "x")
+  if z.dim() != 2:
+    raise ValueError(f"z must have shape [batch, event], got {tuple(z.shape)}")
+  dx = x.shape[-1] if (x is not None and honour_x) else 0
+  d_in = _layers.input_dim_for_latent(transform, z.shape[-1])
+  spec = _layers.trace_chain(transform, d_in, dx)
+  if spec.dim_out != z.shape[-1]:
+    raise ValueError(f"latent has {z.shape[-1]} dims but the flow's latent space has {spec.dim_out}")
+  if fr.is_init:
+    fr.device = z.device
+    B = z.shape[0]
+    return (torch.zeros((B, d_in), dtype=torch.float32, device=z.device),
+            torch.zeros(B, dtype=torch.float32, device=z.device))
+  plan = get_plan(spec, BASE_NONE)
+  flat = hk.pack_params(fr.params, fr.layout, z.device)
+  return plan.forward(z, x if dx > 0 else None, flat)
 
 
 def value_and_grad(fun, has_aux=False):

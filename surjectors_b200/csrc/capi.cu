@@ -354,7 +354,7 @@ static int ensure_device(const SurjPlan* p) {
 }
 
 static int fused_grid(const SurjPlan* p, int64_t B, bool backward) {
-  if (p->exec == 2) return vm_grid(p->vmp, B, backward);
+  if (p->exec == 2) return vm_grid(p->vmp, B, backward ? VM_PROG_BWD : VM_PROG_FWD);
   const int nt = p->fused->nt;
   const int64_t tiles = (B + nt - 1) / nt;
   const int64_t cap = (int64_t)p->n_sm * (backward ? p->bwd_blocks : p->fwd_blocks);
@@ -410,7 +410,7 @@ extern "C" int surj_chain_logprob_fwd(const SurjPlan* plan, SurjStream stream, c
   if (plan->exec == 2) {
     r = ensure_device(plan);
     if (r) return r;
-    return vm_launch(plan->vmp, st, false, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, nullptr, 0.0f, nullptr,
+    return vm_launch(plan->vmp, st, VM_PROG_FWD, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, nullptr, 0.0f, nullptr,
                      z_out, lp_out, nullptr, nullptr, nullptr, 0, batch, fused_grid(plan, batch, false), nullptr, 0);
   }
   if (plan->exec == 1) {
@@ -423,7 +423,7 @@ extern "C" int surj_chain_logprob_fwd(const SurjPlan* plan, SurjStream stream, c
   }
   r = ensure_device(plan);
   if (r) return r;
-  return vm_global_run(plan->vmp, st, false, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, nullptr, 0.0f, nullptr,
+  return vm_global_run(plan->vmp, st, VM_PROG_FWD, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, nullptr, 0.0f, nullptr,
                        z_out, lp_out, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, batch);
 }
 
@@ -525,7 +525,7 @@ static int fused_backward(const SurjPlan* plan, cudaStream_t st, const float* y,
   const int ncb = (np + 1 + 31) / 32;
   const int with_base = plan->base == SURJ_BASE_STANDARD_NORMAL;
   if (plan->exec == 2) {
-    r = vm_launch(plan->vmp, st, true, with_base, y, x, params, g_lp, g_scale, g_z, nullptr, lp_out, g_y, g_x, partials,
+    r = vm_launch(plan->vmp, st, VM_PROG_BWD, with_base, y, x, params, g_lp, g_scale, g_z, nullptr, lp_out, g_y, g_x, partials,
                   npad, batch, grid, tickets, ncb + 1);
     if (r) return r;
   } else {
@@ -556,7 +556,7 @@ extern "C" int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, c
                           workspace_bytes, batch, AdamArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0});
   r = ensure_device(plan);
   if (r) return r;
-  return vm_global_run(plan->vmp, st, true, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z,
+  return vm_global_run(plan->vmp, st, VM_PROG_BWD, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z,
                        nullptr, lp_out, g_y, g_x, g_params, loss_out, workspace, workspace_bytes, batch);
 }
 
@@ -620,6 +620,38 @@ extern "C" int surj_train_step(const SurjPlan* plan, SurjStream stream, const fl
                              nullptr, workspace, workspace_bytes, batch);
   if (r) return r;
   return surj_adam_step(stream, params, g_params, mu, nu, count, plan->n_params, lr, b1, b2, eps, 1.0f);
+}
+
+// Sampling direction: Surjector.forward_and_likelihood_contribution through the Chain in reverse
+// (surjectors/_src/surjectors/chain.py:47-54).  Always runs on the chain program (the generated kernels
+// only cover log_prob and its VJP): fused interpreter kernel when it fits, else the per-op executor.
+extern "C" int surj_chain_forward(const SurjPlan* plan, SurjStream stream, const float* z, const float* x,
+                                  const float* params, float* y_out, float* ld_out, void* workspace,
+                                  size_t workspace_bytes, int64_t batch) {
+  int r = check_io(plan, z, x, params, batch);
+  if (r) return r;
+  if (!y_out || !ld_out) {
+    surj_set_error("y_out and ld_out are required");
+    return SURJ_E_INVALID;
+  }
+  if (!plan->vmp || plan->vmp->ops_gen.empty()) {
+    surj_set_error(plan->vmp ? plan->vmp->gen_why : std::string("chain has no program"));
+    return SURJ_E_UNSUPPORTED;
+  }
+  r = vm_prepare(plan->vmp);
+  if (r) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->vmp->fused_ok && plan->mode != SURJ_MODE_LAYERED)
+    return vm_launch(plan->vmp, st, VM_PROG_GEN, 0, z, x, params, nullptr, 0.0f, nullptr, y_out, ld_out, nullptr, nullptr,
+                     nullptr, 0, batch, vm_grid(plan->vmp, batch, VM_PROG_GEN), nullptr, 0);
+  return vm_global_run(plan->vmp, st, VM_PROG_GEN, 0, z, x, params, nullptr, 0.0f, nullptr, y_out, ld_out, nullptr, nullptr,
+                       nullptr, nullptr, workspace, workspace_bytes, batch);
+}
+
+extern "C" size_t surj_plan_forward_workspace_bytes(const SurjPlan* plan, int64_t batch) {
+  if (!plan || !plan->vmp || batch <= 0) return 0;
+  if (plan->vmp->fused_ok && plan->mode != SURJ_MODE_LAYERED) return 0;
+  return vm_global_workspace_bytes(plan->vmp, batch, false);
 }
 
 // ------------------------------------------------------------- FP32 peak probe

@@ -32,9 +32,9 @@ int surj_cuda_fail(cudaError_t e, const char* what);
 struct VmPlan* vm_compile(const SurjPlan* plan, std::string* why);
 void vm_destroy(struct VmPlan* v);
 int vm_prepare(struct VmPlan* v);
-int vm_grid(const struct VmPlan* v, int64_t B, bool backward);
+int vm_grid(const struct VmPlan* v, int64_t B, int prog);
 int vm_max_grid(const struct VmPlan* v, int64_t B);
-int vm_launch(struct VmPlan* v, cudaStream_t st, bool backward, int with_base, const float* y, const float* x,
+int vm_launch(struct VmPlan* v, cudaStream_t st, int prog, int with_base, const float* y, const float* x,
               const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
               float* g_y, float* g_x, float* partials, int npad, int64_t B, int grid, unsigned* tickets,
               int n_tickets);

@@ -50,8 +50,8 @@ enum : int32_t {
   OP_LINEAR,        // a0 in_row, a1 n_in, a2 w_off, a3 ld, a4 out_row, a5 n_out_pad, a6 b_off, a7 act,
                     // a8 accumulate, a9 pre_row (-1 none)
   OP_AFFINE,        // a0 in_row, a1 out_row, a2 n_t, a3 itab(dims), a4 shift_row, a5 shift_stride, a6 ls_row,
-                    // a7 ls_stride, a8 inner
-  OP_RQS,           // a0 in_row, a1 out_row, a2 n_t, a3 itab(dims), a4 theta_row, a5 K, a6 inner ; f0 lo, f1 hi
+                    // a7 ls_stride, a8 inner, a9 skip_lp (1: do not add the log-det to lp)
+  OP_RQS,           // a0 in_row, a1 out_row, a2 n_t, a3 itab(dims), a4 theta_row, a5 K, a6 inner, a7 skip_lp ; f0 lo, f1 hi
   OP_NORMAL_LP,     // a0 v_row, a1 n_v, a2 mu_row, a3 ls_row
   OP_ADD_SCALAR,    // a0 scalar slot
   OP_BASE,          // a0 z_row, a1 n
@@ -86,7 +86,7 @@ struct ScalarJob {  // prologue: scalars[slot] = sum_i log(par[off + i * stride]
 };
 
 struct Program {            // device-resident (plan-owned) tables
-  const Op* ops;            int32_t n_ops_fwd, n_ops_bwd;   // bwd program = forward sweep + reverse sweep
+  const Op* ops;            int32_t n_ops;                  // the program this launch runs (log_prob, its VJP, or sampling direction)
   const int32_t* stage;     int32_t n_par, n_prim;          // gather table [n_par]
   const int32_t* grad_dst;  const int32_t* grad_aux;        // [n_prim] write-back tables
   const int32_t* itab;      int32_t n_itab;

@@ -270,9 +270,10 @@ int vm_global_launches(const VmPlan* v, int64_t B, bool backward) {
   return 2 + per_chunk * chunks + (backward ? 1 : 0);
 }
 
-int vm_global_run(VmPlan* v, cudaStream_t st, bool backward, int with_base, const float* y, const float* x,
+int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const float* y, const float* x,
                   const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
                   float* g_y, float* g_x, float* g_params, float* loss_out, void* ws, size_t ws_bytes, int64_t B) {
+  const bool backward = prog == VM_PROG_BWD;
   const int C = chunk_cols(B, v->n_rows);
   Carve k = carve(v, ws, C, backward);
   static const int tc_mode = [] {
@@ -293,8 +294,8 @@ int vm_global_run(VmPlan* v, cudaStream_t st, bool backward, int with_base, cons
     return SURJ_E_WORKSPACE;
   }
   const vm::Program& P = v->prog;
-  const std::vector<vm::Op>& ops = backward ? v->ops_bwd : v->ops_fwd;
-  const vm::Op* d_ops = backward ? v->d_ops_bwd : v->d_ops_fwd;
+  const std::vector<vm::Op>& ops = prog == VM_PROG_BWD ? v->ops_bwd : (prog == VM_PROG_GEN ? v->ops_gen : v->ops_fwd);
+  const vm::Op* d_ops = prog == VM_PROG_BWD ? v->d_ops_bwd : (prog == VM_PROG_GEN ? v->d_ops_gen : v->d_ops_fwd);
   const int n_par = (int)v->stage.size();
   vm::Io io;
   io.y = y; io.x = x; io.g_lp = g_lp; io.g_z = g_z; io.z_out = z_out; io.lp_out = lp_out; io.g_y = g_y; io.g_x = g_x;

@@ -143,7 +143,7 @@ vm_kernel(Program P, Io io, const float* __restrict__ params, float* __restrict_
   const int backward = io.backward;
   if (blockIdx.x == 0)  // arm the tickets of the gradient-reduction kernel that follows on the stream
     for (int i = tid; i < n_tickets; i += NT) tickets[i] = 0u;
-  const int n_ops = backward ? P.n_ops_bwd : P.n_ops_fwd;
+  const int n_ops = P.n_ops;
   // carve shared memory (every region 16-byte aligned)
   auto align4 = [](int n) { return (n + 3) & ~3; };
   Op* sops = reinterpret_cast<Op*>(smem_raw);

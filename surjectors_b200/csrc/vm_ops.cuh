@@ -89,6 +89,7 @@ template <int NT, int S>
 VM_DEV void op_affine(Ctx<NT, S>& c, const Op& op) {
   const int in_row = op.a[0], out_row = op.a[1], n_t = op.a[2], it = op.a[3], sh = op.a[4], ss = op.a[5], ls = op.a[6],
             lss = op.a[7], inner = op.a[8];
+  const float lpw = op.a[9] ? 0.0f : 1.0f;
   for (int k = 0; k < n_t; ++k) {
     const int d = c.itab[it + k];
 #pragma unroll
@@ -97,10 +98,10 @@ VM_DEV void op_affine(Ctx<NT, S>& c, const Op& op) {
       float z;
       if (inner == INNER_AFFINE) {  // ScalarAffine(m, exp(l)).inverse: z = (y - m) e^{-l}, ld = -l
         z = (y - m) * expf(-l);
-        c.lp[s] -= l;
+        c.lp[s] -= lpw * l;
       } else {  // Inverse(ScalarAffine).inverse = forward: z = e^{l} y + m, ld = +l
         z = fmaf(expf(l), y, m);
-        c.lp[s] += l;
+        c.lp[s] += lpw * l;
       }
       c.row(out_row + d)[s * NT] = z;
     }
@@ -156,7 +157,7 @@ VM_DEV void op_rqs(Ctx<NT, S>& c, const Op& op) {
       float out, ld;
       rqs_eval(b, K, op.f0, op.f1, v, forward, out, ld);
       c.row(out_row + d)[s * NT] = out;
-      c.lp[s] += ld;
+      if (!op.a[7]) c.lp[s] += ld;
     }
   }
 }

@@ -219,12 +219,15 @@ struct LayerCode {
   std::vector<Op> fwd;    // inference-mode forward
   std::vector<Op> train;  // training-mode forward recompute (keeps pre-activations)
   std::vector<Op> bwd;    // backward, assumes `train` just ran with the same scratch layout
+  std::vector<Op> gen;    // sampling direction: forward_and_likelihood_contribution (E[l+1] -> E[l])
+  bool gen_ok = false;
 };
 
 }  // namespace
 
-static size_t vm_smem_bytes(const VmPlan& v, bool backward, int T) {
-  const size_t n_ops = backward ? v.ops_bwd.size() : v.ops_fwd.size();
+static size_t vm_smem_bytes(const VmPlan& v, int prog, int T) {
+  const bool backward = prog == VM_PROG_BWD;
+  const size_t n_ops = prog == VM_PROG_BWD ? v.ops_bwd.size() : (prog == VM_PROG_GEN ? v.ops_gen.size() : v.ops_fwd.size());
   size_t b = n_ops * sizeof(Op);
   b += (size_t)pad4((int)v.itab.size()) * 4;
   b += (size_t)pad4((int)v.stage.size()) * 4;
@@ -350,6 +353,21 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
             C.fwd.push_back(mk(vm::OP_NORMAL_LP, {Ein + K, nv, thd, thd + nv}));
           }
         }
+        if (!funnel) {  // sampling direction (masked_coupling.py:59-71): same conditioner on the pass-through dims of z,
+                        // inner bijector in the other direction (inner ^ 1 swaps X <-> Inverse(X))
+          B.scratch_reset();
+          std::vector<int> gsrc;
+          for (int d : pass) gsrc.push_back(Eout + d);
+          xrows(gsrc);
+          const int m_row = B.scratch(pad8(cin));
+          if (n_pass > 0) C.gen.push_back(mk(vm::OP_COPY, {Ein, Eout, D}));
+          C.gen.push_back(mk(vm::OP_GATHER, {m_row, cin, B.tab(gsrc)}));
+          std::vector<NetRows> rows = emit_mlp_fwd(B, C.gen, mats, Ld.conditioner.act, m_row, false);
+          const int th = rows.back().post_row;
+          if (rqs) C.gen.push_back(mk(vm::OP_RQS, {Eout, Ein, n_t, t_dims, th, Kb, Ld.inner ^ 1, 0}, lo, hi));
+          else C.gen.push_back(mk(vm::OP_AFFINE, {Eout, Ein, n_t, t_dims, th, 1, th + n_t, 1, Ld.inner ^ 1, 0}));
+          C.gen_ok = true;
+        }
         {  // training forward + backward
           B.scratch_reset();
           std::vector<NetRows> rows, drows;
@@ -419,6 +437,36 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
             const int thd = drows.back().post_row;
             C.fwd.push_back(mk(vm::OP_NORMAL_LP, {Ein + K, nv, thd, thd + nv}));
           }
+        }
+        if (!funnel) {  // sampling direction (masked_autoregressive.py:63-71): y = 0, then D passes of
+                        // y = inner(MADE(y, x)).forward(z); the log-det of the last pass is the contribution
+          B.scratch_reset();
+          std::vector<Op> one;
+          {
+            // the MADE reads the current y estimate (rows Ein) instead of the layer input
+            MadeRows R;
+            R.cc_row = -1;
+            R.h0_row = B.scratch(mm.l0.ld);
+            R.p0_row = mm.has_ctx ? B.scratch(mm.l0.ld) : -1;
+            if (mm.has_ctx) {
+              R.cc_row = B.scratch(pad8(ctxw));
+              one.push_back(mk(vm::OP_GATHER, {R.cc_row, ctxw, B.tab(csrc)}));
+              one.push_back(lin_fwd(mm.l0, Ein, R.p0_row, vm::ACT_IDENTITY, 0, -1));
+              one.push_back(lin_fwd(mm.ctx, R.cc_row, R.h0_row, act, 1, R.p0_row));
+            } else {
+              one.push_back(lin_fwd(mm.l0, Ein, R.h0_row, act, 0, -1));
+            }
+            R.rest = emit_mlp_fwd(B, one, mm.rest, mm.rest_acts.data(), R.h0_row, false);
+            const int th = R.rest.back().post_row;
+            if (rqs) one.push_back(mk(vm::OP_RQS, {Eout, Ein, Dm, t_dims, th, Kb, Ld.inner ^ 1, 1}, lo, hi));
+            else one.push_back(mk(vm::OP_AFFINE, {Eout, Ein, Dm, t_dims, th, 2, th + 1, 2, Ld.inner ^ 1, 1}));
+          }
+          C.gen.push_back(mk(vm::OP_ZERO, {Ein, Dm}));
+          for (int it = 0; it < Dm; ++it) {
+            C.gen.insert(C.gen.end(), one.begin(), one.end());
+            if (it == Dm - 1) C.gen.back().a[rqs ? 7 : 9] = 0;  // only the last pass contributes its log-det
+          }
+          C.gen_ok = true;
         }
         {
           B.scratch_reset();
@@ -522,6 +570,10 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
         for (int d = 0; d < D; ++d) { f[d] = Ein + inv[d]; b[d] = Gout + Ld.permutation[d]; }
         C.fwd.push_back(mk(vm::OP_GATHER, {Eout, D, B.tab(f)}));   // z = y[..., inv]  (permutation.py:37)
         C.bwd.push_back(mk(vm::OP_GATHER, {Gin, D, B.tab(b)}));    // g_y = g_z[..., perm]
+        std::vector<int> gsel(D);
+        for (int d = 0; d < D; ++d) gsel[d] = Eout + Ld.permutation[d];
+        C.gen.push_back(mk(vm::OP_GATHER, {Ein, D, B.tab(gsel)}));  // y = z[..., perm]  (permutation.py:27-28)
+        C.gen_ok = true;
         break;
       }
       default:
@@ -549,6 +601,24 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
   }
   v->ops_bwd.push_back(mk(vm::OP_STORE, {G[L & 1], plan->dim_in, 1}));
   if (dx > 0) v->ops_bwd.push_back(mk(vm::OP_STORE, {GX, dx, 2}));
+  // sampling direction: latent z -> y through the layers in reverse (chain.py:47-54); only when every layer
+  // has a forward (LULinear has none upstream, lu_linear.py:92-93; surjections need a decoder sample)
+  bool gen_ok = true;
+  for (int l = 0; l < L; ++l)
+    if (!code[l].gen_ok) {
+      gen_ok = false;
+      char buf[96];
+      snprintf(buf, sizeof buf, "layer %d (kind %d) has no forward / sampling direction here", l, plan->layers[l].kind);
+      v->gen_why = buf;
+      break;
+    }
+  if (gen_ok) {
+    v->ops_gen.push_back(mk(vm::OP_LOAD, {E[L], dz, 0}));
+    if (dx > 0) v->ops_gen.push_back(mk(vm::OP_LOAD, {X, dx, 1}));
+    for (int l = L - 1; l >= 0; --l) v->ops_gen.insert(v->ops_gen.end(), code[l].gen.begin(), code[l].gen.end());
+    v->ops_gen.push_back(mk(vm::OP_STORE, {E[0], plan->dim_in, 0}));
+    v->ops_gen.push_back(mk(vm::OP_STORE_LP, {}));
+  }
 
   while (B.stage.size() & 3) B.push(vm::STAGE_ZERO, -1);
   v->stage = B.stage; v->grad_dst = B.grad_dst; v->grad_aux = B.grad_aux; v->itab = B.itab; v->sjobs = B.sjobs;
@@ -561,14 +631,15 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
   const size_t cap = 227 * 1024, want = 110 * 1024;
   const int cands[][2] = {{64, 1}, {32, 1}};
   for (int ci = 0; ci < 2 && !v->fused_ok; ++ci) {
-    const size_t need = vm_smem_bytes(*v, true, cands[ci][0] * cands[ci][1]);
+    const size_t need = vm_smem_bytes(*v, VM_PROG_BWD, cands[ci][0] * cands[ci][1]);
     if (need <= want || (ci == 1 && need <= cap)) {
       v->nt = cands[ci][0]; v->s = cands[ci][1]; v->fused_ok = true;
     }
   }
   if (!v->fused_ok) v->fused_why = "parameters + activations of one tile exceed the shared memory of an SM";
-  v->smem_fwd = vm_smem_bytes(*v, false, v->nt * v->s);
-  v->smem_bwd = vm_smem_bytes(*v, true, v->nt * v->s);
+  v->smem_fwd = vm_smem_bytes(*v, VM_PROG_FWD, v->nt * v->s);
+  v->smem_bwd = vm_smem_bytes(*v, VM_PROG_BWD, v->nt * v->s);
+  v->smem_gen = vm_smem_bytes(*v, VM_PROG_GEN, v->nt * v->s);
   return v;
 }
 
@@ -593,14 +664,16 @@ int vm_prepare(VmPlan* v) {
   cudaDeviceGetAttribute(&v->n_sm, cudaDevAttrMultiProcessorCount, dev);
   auto a16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
   const size_t b_fwd = a16(v->ops_fwd.size() * sizeof(Op)), b_bwd = a16(v->ops_bwd.size() * sizeof(Op));
+  const size_t b_gen = a16(std::max<size_t>(v->ops_gen.size(), 1) * sizeof(Op));
   const size_t b_stage = a16(v->stage.size() * 4), b_itab = a16(std::max<size_t>(v->itab.size(), 1) * 4);
   const size_t b_sj = a16(std::max<size_t>(v->sjobs.size(), 1) * sizeof(vm::ScalarJob));
-  const size_t total = b_fwd + b_bwd + 3 * b_stage + b_itab + b_sj;
+  const size_t total = b_fwd + b_bwd + b_gen + 3 * b_stage + b_itab + b_sj;
   std::vector<unsigned char> host(total, 0);
   size_t o = 0;
   auto put = [&](const void* p, size_t n, size_t slot) { if (n) std::memcpy(host.data() + o, p, n); const size_t r = o; o += slot; return r; };
   const size_t o_fwd = put(v->ops_fwd.data(), v->ops_fwd.size() * sizeof(Op), b_fwd);
   const size_t o_bwd = put(v->ops_bwd.data(), v->ops_bwd.size() * sizeof(Op), b_bwd);
+  const size_t o_gen = put(v->ops_gen.data(), v->ops_gen.size() * sizeof(Op), b_gen);
   const size_t o_stage = put(v->stage.data(), v->stage.size() * 4, b_stage);
   const size_t o_gd = put(v->grad_dst.data(), v->grad_dst.size() * 4, b_stage);
   const size_t o_ga = put(v->grad_aux.data(), v->grad_aux.size() * 4, b_stage);
@@ -613,9 +686,10 @@ int vm_prepare(VmPlan* v) {
   unsigned char* d = (unsigned char*)v->d_blob;
   v->d_ops_fwd = (const Op*)(d + o_fwd);
   v->d_ops_bwd = (const Op*)(d + o_bwd);
+  v->d_ops_gen = (const Op*)(d + o_gen);
   vm::Program& P = v->prog;
   P.ops = nullptr;
-  P.n_ops_fwd = (int)v->ops_fwd.size(); P.n_ops_bwd = (int)v->ops_bwd.size();
+  P.n_ops = 0;
   P.stage = (const int32_t*)(d + o_stage); P.n_par = (int)v->stage.size(); P.n_prim = (int)v->stage.size();
   P.grad_dst = (const int32_t*)(d + o_gd); P.grad_aux = (const int32_t*)(d + o_ga);
   P.itab = (const int32_t*)(d + o_it); P.n_itab = (int)v->itab.size();
@@ -630,7 +704,7 @@ int vm_prepare(VmPlan* v) {
   // different footprints can share the kernel
   int optin = 227 * 1024;
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if ((size_t)optin < std::max(v->smem_fwd, v->smem_bwd)) {
+  if ((size_t)optin < std::max(std::max(v->smem_fwd, v->smem_bwd), v->smem_gen)) {
     surj_set_error("fused kernel needs more shared memory than this device offers");
     return SURJ_E_CUDA;
   }
@@ -638,6 +712,7 @@ int vm_prepare(VmPlan* v) {
   if (e != cudaSuccess) return surj_cuda_fail(e, "cudaFuncSetAttribute(vm_kernel)");
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v->occ_fwd, k, v->nt, v->smem_fwd);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v->occ_bwd, k, v->nt, v->smem_bwd);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v->occ_gen, k, v->nt, v->smem_gen);
   if (e != cudaSuccess) return surj_cuda_fail(e, "occupancy(vm_kernel)");
   if (v->occ_fwd < 1 || v->occ_bwd < 1) {
     surj_set_error("vm_kernel does not fit on an SM");
@@ -647,10 +722,10 @@ int vm_prepare(VmPlan* v) {
   return SURJ_OK;
 }
 
-int vm_grid(const VmPlan* v, int64_t B, bool backward) {
+int vm_grid(const VmPlan* v, int64_t B, int prog) {
   const int T = v->nt * v->s;
   const int64_t tiles = (B + T - 1) / T;
-  const int64_t cap = (int64_t)v->n_sm * (backward ? v->occ_bwd : v->occ_fwd);
+  const int64_t cap = (int64_t)v->n_sm * (prog == VM_PROG_BWD ? v->occ_bwd : (prog == VM_PROG_GEN ? v->occ_gen : v->occ_fwd));
   return (int)std::min<int64_t>(tiles, cap);
 }
 
@@ -660,17 +735,19 @@ int vm_max_grid(const VmPlan* v, int64_t B) {  // upper bound usable before a de
   return (int)std::min<int64_t>(tiles, 148 * 16);
 }
 
-int vm_launch(VmPlan* v, cudaStream_t st, bool backward, int with_base, const float* y, const float* x,
+int vm_launch(VmPlan* v, cudaStream_t st, int prog, int with_base, const float* y, const float* x,
               const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
               float* g_y, float* g_x, float* partials, int npad, int64_t B, int grid, unsigned* tickets,
               int n_tickets) {
+  const bool backward = prog == VM_PROG_BWD;
   vm::Program P = v->prog;
-  P.ops = backward ? v->d_ops_bwd : v->d_ops_fwd;
+  P.ops = backward ? v->d_ops_bwd : (prog == VM_PROG_GEN ? v->d_ops_gen : v->d_ops_fwd);
+  P.n_ops = (int)(backward ? v->ops_bwd.size() : (prog == VM_PROG_GEN ? v->ops_gen.size() : v->ops_fwd.size()));
   vm::Io io;
   io.y = y; io.x = x; io.g_lp = g_lp; io.g_z = g_z; io.z_out = z_out; io.lp_out = lp_out; io.g_y = g_y; io.g_x = g_x;
   io.g_scale = g_scale; io.with_base = with_base; io.backward = backward ? 1 : 0;
   VmKernel k = vm_kernel_for(v->nt, v->s);
-  k<<<grid, v->nt, backward ? v->smem_bwd : v->smem_fwd, st>>>(P, io, params, partials, npad, (long long)B, tickets,
+  k<<<grid, v->nt, backward ? v->smem_bwd : (prog == VM_PROG_GEN ? v->smem_gen : v->smem_fwd), st>>>(P, io, params, partials, npad, (long long)B, tickets,
                                                                 n_tickets);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return surj_cuda_fail(e, "vm_kernel launch");

@@ -7,7 +7,8 @@
 #include "vm.cuh"
 
 struct VmPlan {
-  std::vector<vm::Op> ops_fwd, ops_bwd;
+  std::vector<vm::Op> ops_fwd, ops_bwd, ops_gen;  // log_prob, its VJP, sampling direction (empty: unsupported)
+  std::string gen_why;
   std::vector<int32_t> stage, grad_dst, grad_aux, itab;
   std::vector<vm::ScalarJob> sjobs;
   int n_scalars = 0, n_rows = 0;
@@ -16,19 +17,21 @@ struct VmPlan {
   bool fused_ok = false;
   std::string fused_why;
   int nt = 64, s = 1;
-  size_t smem_fwd = 0, smem_bwd = 0;
+  size_t smem_fwd = 0, smem_bwd = 0, smem_gen = 0;
   // device state (uploaded lazily on the first launch)
   bool uploaded = false;
   void* d_blob = nullptr;
   vm::Program prog{};
   const vm::Op* d_ops_fwd = nullptr;
   const vm::Op* d_ops_bwd = nullptr;
-  int n_sm = 148, occ_fwd = 1, occ_bwd = 1;
+  const vm::Op* d_ops_gen = nullptr;
+  int n_sm = 148, occ_fwd = 1, occ_bwd = 1, occ_gen = 1;
 };
 
 // vm_global.cu
+enum { VM_PROG_FWD = 0, VM_PROG_BWD = 1, VM_PROG_GEN = 2 };
 size_t vm_global_workspace_bytes(const VmPlan* v, int64_t B, bool backward);
 int vm_global_launches(const VmPlan* v, int64_t B, bool backward);
-int vm_global_run(VmPlan* v, cudaStream_t st, bool backward, int with_base, const float* y, const float* x,
+int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const float* y, const float* x,
                   const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
                   float* g_y, float* g_x, float* g_params, float* loss_out, void* ws, size_t ws_bytes, int64_t B);

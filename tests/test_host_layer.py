@@ -183,8 +183,8 @@ def test_no_cpu_fallback():
   params = m.init(0, method="log_prob", y=y)
   with pytest.raises(_abi.SurjError, match="no CPU fallback"):
     m.apply(params, None, method="log_prob", y=y)
-  with pytest.raises(NotImplementedError):  # sampling direction is section 8f
-    m.apply(params, None, method="sample", sample_shape=(2,))
+  with pytest.raises(NotImplementedError):  # sampling through a surjection (decoder sampling) is section 8f, next
+    m.apply(params, 0, method="sample", sample_shape=(2,))
 
 
 def test_bad_descriptor_is_rejected_by_the_c_abi():
