@@ -182,6 +182,22 @@ int surj_train_step(const SurjPlan* plan, SurjStream stream, const float* y, con
                     float g_scale, float* g_params, float* mu, float* nu, int32_t* count, float lr, float b1, float b2,
                     float eps, float* loss_out, void* workspace, size_t workspace_bytes, int64_t batch);
 
+/* --- data-parallel training: one process per GPU, batch sharded, parameters replicated.
+ * For KB-sized gradients the all-reduce is fused into the gradient-reduction kernel over NVLink peer memory:
+ * surj_dp_create allocates this rank's mailbox and returns its CUDA IPC handle; the handles of all ranks (in rank
+ * order, exchanged by the host, e.g. torch.distributed.all_gather) go to surj_dp_connect; surj_train_step_dp is
+ * surj_train_step on the local shard with the sum over ranks inside (2 launches, no NCCL call).  Every rank must
+ * call it the same number of times.  surj_dp_error() != 0 reports a peer that did not arrive within ~2 s. */
+#define SURJ_IPC_HANDLE_BYTES 64
+typedef struct SurjDp SurjDp;
+int surj_dp_create(int32_t rank, int32_t world, int64_t n_params, SurjDp** out, unsigned char* handle_out);
+int surj_dp_connect(SurjDp* dp, const unsigned char* handles);
+void surj_dp_destroy(SurjDp* dp);
+int32_t surj_dp_error(const SurjDp* dp);
+int surj_train_step_dp(const SurjPlan* plan, SurjDp* dp, SurjStream stream, const float* y, const float* x, float* params,
+                       float g_scale, float* g_params, float* mu, float* nu, int32_t* count, float lr, float b1,
+                       float b2, float eps, float* loss_out, void* workspace, size_t workspace_bytes, int64_t batch);
+
 /* --- helpers */
 /* TFP _make_dense_autoregressive_masks restated; writes n_hidden+1 masks ([in, out] row-major,
  * bytes 0/1) back to back into out (size queried by passing out == NULL). */

@@ -106,6 +106,13 @@ _SIGNATURES = {
   "surj_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
+  "surj_dp_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+  "surj_dp_connect": (C.c_int, [C.c_void_p, C.c_char_p]),
+  "surj_dp_destroy": (None, [C.c_void_p]),
+  "surj_dp_error": (C.c_int32, [C.c_void_p]),
+  "surj_train_step_dp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                   C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
   "surj_made_masks": (C.c_int64, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8)]),
   "surj_permutation_inverse": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
   "surj_bench_fp32_peak": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]),

@@ -161,6 +161,21 @@ def _plan_train_step(self, y, x, flat, g_scale, grads, opt, loss_out):
 Plan.train_step = _plan_train_step
 
 
+def _plan_train_step_dp(self, dp, y, x, flat, g_scale, grads, opt, loss_out):
+  """surj_train_step_dp: the same two launches with the sum over ranks fused in (NVLink peer mailboxes)."""
+  B = y.shape[0]
+  _check_inputs(self, y, x, flat)
+  ws, n = self.workspace(B, True, y.device)
+  st = self._lib.surj_train_step_dp(
+    self._h, dp.handle, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), float(g_scale), grads.data_ptr(),
+    opt.mu.data_ptr(), opt.nu.data_ptr(), opt.count.data_ptr(), opt.lr, opt.b1, opt.b2, opt.eps, _ptr(loss_out),
+    ws.data_ptr(), n, B)
+  _abi.check(st, "surj_train_step_dp")
+
+
+Plan.train_step_dp = _plan_train_step_dp
+
+
 def _ptr(t):
   return None if t is None else t.data_ptr()
 

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <vector>
 #include <string>
 
 #include "plan.h"
@@ -438,18 +439,38 @@ struct AdamArgs {
   float* params; float* mu; float* nu; int32_t* count;
   float lr, b1, b2, eps;
 };
+// Data-parallel exchange over NVLink peer memory (SurjDp): every rank owns a mailbox
+// box[2][world][npad] + flags[2][world][column blocks] that its peers write into directly.
+struct DpArgs {
+  float* const* peer_box;       // [world] device pointers to the peers' mailboxes (nullptr: single GPU)
+  unsigned* const* peer_flags;  // [world]
+  float* my_box; unsigned* my_flags;
+  int rank, world;
+  int* err;                     // set to 1 if a peer did not arrive in time
+};
 constexpr int RSL = 8;
+
+__device__ __forceinline__ void adam_update(const AdamArgs& ad, int col, float g, int t) {
+  const float c1 = 1.0f / (1.0f - powf(ad.b1, (float)t)), c2 = 1.0f / (1.0f - powf(ad.b2, (float)t));
+  const float m = ad.b1 * ad.mu[col] + (1.0f - ad.b1) * g;
+  const float v = ad.b2 * ad.nu[col] + (1.0f - ad.b2) * g * g;
+  ad.mu[col] = m;
+  ad.nu[col] = v;
+  ad.params[col] -= ad.lr * (m * c1) / (sqrtf(v * c2) + ad.eps);
+}
 
 __global__ void __launch_bounds__(256)
 surj_reduce_partials_kernel(const float* __restrict__ partials, int nrows, int npad, int np,
                             float* __restrict__ slices, unsigned* __restrict__ tickets,
-                            float* __restrict__ g_params, float* __restrict__ loss_out, float loss_scale, AdamArgs ad) {
+                            float* __restrict__ g_params, float* __restrict__ loss_out, float loss_scale, AdamArgs ad,
+                            DpArgs dp) {
   __shared__ float red[8][33];
   __shared__ unsigned s_ticket;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
   const int per = (nrows + RSL - 1) / RSL;
   const int r0 = blockIdx.y * per, r1 = min(nrows, r0 + per);
+  const bool multi = dp.peer_box != nullptr;
   float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
   if (col <= np) {
     int r = r0 + w;
@@ -473,21 +494,48 @@ surj_reduce_partials_kernel(const float* __restrict__ partials, int nrows, int n
     __syncwarp();
     if (s_ticket == RSL - 1) {  // last slice of this column block: finish the columns
       __threadfence();
-      if (col <= np) {
-        float g = 0.0f;
+      const bool valid = col <= np;  // the last column block is partly empty; all 32 lanes stay converged
+      float g = 0.0f;
+      if (valid) {
 #pragma unroll
         for (int k = 0; k < RSL; ++k) g += __ldcg(slices + (size_t)k * npad + col);
+      }
+      if (multi) {
+        // Data parallel: this warp finishes its 32 columns across ALL ranks.  My shard's sums go straight
+        // into every rank's mailbox (NVLink peer stores), a per-column-block flag says "delivered", then the
+        // peers' contributions are summed in rank order (bit-identical on every rank) and Adam is applied.
+        const int t = *ad.count + 1, buf = t & 1;
+        if (valid) {
+          const size_t slot = ((size_t)buf * dp.world + dp.rank) * npad + col;
+          for (int p = 0; p < dp.world; ++p) dp.peer_box[p][slot] = g;
+        }
+        __threadfence_system();
+        __syncwarp();
+        const size_t fslot = ((size_t)buf * dp.world) * gridDim.x + blockIdx.x;
+        for (int r = lane; r < dp.world; r += 32) {
+          volatile unsigned* f = dp.peer_flags[r] + fslot + (size_t)dp.rank * gridDim.x;
+          *f = (unsigned)t;  // rank `rank` has delivered column block blockIdx.x of step t
+        }
+        for (int r = lane; r < dp.world; r += 32) {
+          volatile unsigned* mine = dp.my_flags + fslot + (size_t)r * gridDim.x;
+          const long long t0 = clock64();
+          while (*mine != (unsigned)t) {
+            if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone; report instead of hanging the GPU
+              *dp.err = 1;
+              break;
+            }
+          }
+        }
+        __threadfence_system();
+        __syncwarp();
+        g = 0.0f;
+        if (valid)
+          for (int r = 0; r < dp.world; ++r) g += __ldcg(dp.my_box + ((size_t)buf * dp.world + r) * npad + col);
+      }
+      if (valid) {
         if (col < np) {
           g_params[col] = g;
-          if (ad.params != nullptr) {  // optax.adam (examples/coupling_inference_surjection.py:78,88-89)
-            const int t = *ad.count + 1;
-            const float c1 = 1.0f / (1.0f - powf(ad.b1, (float)t)), c2 = 1.0f / (1.0f - powf(ad.b2, (float)t));
-            const float m = ad.b1 * ad.mu[col] + (1.0f - ad.b1) * g;
-            const float v = ad.b2 * ad.nu[col] + (1.0f - ad.b2) * g * g;
-            ad.mu[col] = m;
-            ad.nu[col] = v;
-            ad.params[col] -= ad.lr * (m * c1) / (sqrtf(v * c2) + ad.eps);
-          }
+          if (ad.params != nullptr) adam_update(ad, col, g, *ad.count + 1);  // optax.adam
         } else if (loss_out) {
           *loss_out = loss_scale * g;
         }
@@ -509,7 +557,7 @@ static size_t fused_bwd_workspace(int64_t rows, int npad, int np) {
 static int fused_backward(const SurjPlan* plan, cudaStream_t st, const float* y, const float* x, const float* params,
                           const float* g_lp, float g_scale, const float* g_z, float* g_params, float* loss_out,
                           float* lp_out, float* g_y, float* g_x, void* workspace, size_t workspace_bytes, int64_t batch,
-                          AdamArgs ad) {
+                          AdamArgs ad, DpArgs dp) {
   int r = ensure_device(plan);
   if (r) return r;
   const int grid = fused_grid(plan, batch, true);
@@ -534,7 +582,7 @@ static int fused_backward(const SurjPlan* plan, cudaStream_t st, const float* y,
     if (e != cudaSuccess) return surj_cuda_fail(e, "chain_bwd_kernel launch");
   }
   surj_reduce_partials_kernel<<<dim3(ncb, RSL), 256, 0, st>>>(partials, grid, npad, np, slices, tickets, g_params,
-                                                             loss_out, g_lp ? 1.0f : g_scale, ad);
+                                                             loss_out, g_lp ? 1.0f : g_scale, ad, dp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return surj_cuda_fail(e, "reduce_partials launch");
   return SURJ_OK;
@@ -553,7 +601,7 @@ extern "C" int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, c
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->exec == 1 || plan->exec == 2)
     return fused_backward(plan, st, y, x, params, g_lp, g_scale, g_z, g_params, loss_out, lp_out, g_y, g_x, workspace,
-                          workspace_bytes, batch, AdamArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0});
+                          workspace_bytes, batch, AdamArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0}, DpArgs{});
   r = ensure_device(plan);
   if (r) return r;
   return vm_global_run(plan->vmp, st, VM_PROG_BWD, plan->base == SURJ_BASE_STANDARD_NORMAL, y, x, params, g_lp, g_scale, g_z,
@@ -615,7 +663,7 @@ extern "C" int surj_train_step(const SurjPlan* plan, SurjStream stream, const fl
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->exec == 1 || plan->exec == 2)
     return fused_backward(plan, st, y, x, params, nullptr, g_scale, nullptr, g_params, loss_out, nullptr, nullptr,
-                          nullptr, workspace, workspace_bytes, batch, AdamArgs{params, mu, nu, count, lr, b1, b2, eps});
+                          nullptr, workspace, workspace_bytes, batch, AdamArgs{params, mu, nu, count, lr, b1, b2, eps}, DpArgs{});
   r = surj_chain_logprob_bwd(plan, stream, y, x, params, nullptr, g_scale, nullptr, g_params, loss_out, nullptr, nullptr,
                              nullptr, workspace, workspace_bytes, batch);
   if (r) return r;
@@ -652,6 +700,113 @@ extern "C" size_t surj_plan_forward_workspace_bytes(const SurjPlan* plan, int64_
   if (!plan || !plan->vmp || batch <= 0) return 0;
   if (plan->vmp->fused_ok && plan->mode != SURJ_MODE_LAYERED) return 0;
   return vm_global_workspace_bytes(plan->vmp, batch, false);
+}
+
+// ---------------------------------------------------------- data-parallel train step
+// Replicated parameters, sharded batch: the flat gradient (+ loss) of every rank must be summed before the
+// Adam update.  For the KB-sized gradients of the small-network configs an NCCL
+// all-reduce (launch + protocol latency) costs as much as a fifth of the step, so the exchange is fused into
+// the gradient-reduction kernel: each rank stores its reduced gradient directly into every peer's mailbox
+// (NVLink / NVSwitch peer memory), raises a flag, waits for the peers' flags, sums the mailbox in rank order
+// (bit-identical on all ranks) and applies Adam -- backward kernel + ONE kernel, no NCCL call in the step.
+struct SurjDp {
+  int rank = 0, world = 1, npad = 0;
+  float* box = nullptr;         // [2][world][npad]
+  unsigned* flags = nullptr;    // [2][world][column blocks], same allocation as box
+  std::vector<void*> opened;    // peers' mappings (cudaIpcOpenMemHandle)
+  float** d_peer_box = nullptr;
+  unsigned** d_peer_flags = nullptr;
+  int* d_err = nullptr;
+  size_t box_floats = 0;
+};
+
+extern "C" int surj_dp_create(int32_t rank, int32_t world, int64_t n_params, SurjDp** out, unsigned char* handle_out) {
+  if (!out || !handle_out || world < 1 || rank < 0 || rank >= world || n_params <= 0) {
+    surj_set_error("surj_dp_create: bad arguments");
+    return SURJ_E_INVALID;
+  }
+  SurjDp* d = new SurjDp();
+  d->rank = rank; d->world = world;
+  d->npad = (int)((n_params + 1 + 3) / 4 * 4);
+  d->box_floats = (size_t)2 * world * d->npad;
+  const size_t ncb = (size_t)(n_params + 1 + 31) / 32;
+  const size_t bytes = d->box_floats * 4 + (size_t)2 * world * ncb * 4 + 64;
+  cudaError_t e = cudaMalloc((void**)&d->box, bytes);
+  if (e == cudaSuccess) e = cudaMemset(d->box, 0, bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d->d_err, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(d->d_err, 0, sizeof(int));
+  if (e != cudaSuccess) { delete d; return surj_cuda_fail(e, "surj_dp_create"); }
+  d->flags = (unsigned*)(d->box + d->box_floats);
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, d->box);
+  if (e != cudaSuccess) { delete d; return surj_cuda_fail(e, "cudaIpcGetMemHandle"); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == SURJ_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle_out, &h, sizeof h);
+  *out = d;
+  return SURJ_OK;
+}
+
+extern "C" int surj_dp_connect(SurjDp* d, const unsigned char* handles) {
+  if (!d || !handles) { surj_set_error("surj_dp_connect: bad arguments"); return SURJ_E_INVALID; }
+  std::vector<float*> boxes(d->world);
+  std::vector<unsigned*> flags(d->world);
+  for (int r = 0; r < d->world; ++r) {
+    if (r == d->rank) { boxes[r] = d->box; flags[r] = d->flags; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * SURJ_IPC_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return surj_cuda_fail(e, "cudaIpcOpenMemHandle (peer mailbox)");
+    d->opened.push_back(p);
+    boxes[r] = (float*)p;
+    flags[r] = (unsigned*)((float*)p + d->box_floats);
+  }
+  cudaError_t e = cudaMalloc((void**)&d->d_peer_box, sizeof(float*) * d->world);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d->d_peer_flags, sizeof(unsigned*) * d->world);
+  if (e == cudaSuccess) e = cudaMemcpy(d->d_peer_box, boxes.data(), sizeof(float*) * d->world, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d->d_peer_flags, flags.data(), sizeof(unsigned*) * d->world, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return surj_cuda_fail(e, "surj_dp_connect");
+  return SURJ_OK;
+}
+
+extern "C" void surj_dp_destroy(SurjDp* d) {
+  if (!d) return;
+  for (void* p : d->opened) cudaIpcCloseMemHandle(p);
+  if (d->d_peer_box) cudaFree(d->d_peer_box);
+  if (d->d_peer_flags) cudaFree(d->d_peer_flags);
+  if (d->d_err) cudaFree(d->d_err);
+  if (d->box) cudaFree(d->box);
+  delete d;
+}
+
+extern "C" int32_t surj_dp_error(const SurjDp* d) {  // synchronises: for tests / end of run, not the hot path
+  int v = 0;
+  if (d && d->d_err) cudaMemcpy(&v, d->d_err, sizeof v, cudaMemcpyDeviceToHost);
+  return v;
+}
+
+extern "C" int surj_train_step_dp(const SurjPlan* plan, SurjDp* d, SurjStream stream, const float* y, const float* x,
+                                  float* params, float g_scale, float* g_params, float* mu, float* nu, int32_t* count,
+                                  float lr, float b1, float b2, float eps, float* loss_out, void* workspace,
+                                  size_t workspace_bytes, int64_t batch) {
+  int r = check_io(plan, y, x, params, batch);
+  if (r) return r;
+  if (!d || !d->d_peer_box || !g_params || !mu || !nu || !count) {
+    surj_set_error("surj_train_step_dp: connect the SurjDp first; g_params, mu, nu and count are required");
+    return SURJ_E_INVALID;
+  }
+  if (plan->exec != 1 && plan->exec != 2) {
+    surj_set_error("the fused peer-memory exchange serves the fused executors; use an all-reduce for wide networks");
+    return SURJ_E_UNSUPPORTED;
+  }
+  if (d->npad != fused_npad(plan)) {
+    surj_set_error("SurjDp was created for a different parameter count");
+    return SURJ_E_INVALID;
+  }
+  DpArgs dp{d->d_peer_box, d->d_peer_flags, d->box, d->flags, d->rank, d->world, d->d_err};
+  return fused_backward(plan, (cudaStream_t)stream, y, x, params, nullptr, g_scale, nullptr, g_params, loss_out, nullptr,
+                        nullptr, nullptr, workspace, workspace_bytes, batch, AdamArgs{params, mu, nu, count, lr, b1, b2, eps},
+                        dp);
 }
 
 // ------------------------------------------------------------- FP32 peak probe

@@ -28,3 +28,37 @@ def adam_reference_(p, g, mu, nu, t, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
   c1, c2 = 1.0 / (1.0 - b1**t), 1.0 / (1.0 - b2**t)
   p.sub_(lr * (mu * c1) / (torch.sqrt(nu * c2) + eps))
   return p
+
+
+class PeerExchange:
+  """The fused alternative to the all-reduce for KB-sized gradients: every rank's reduced gradient is stored
+  straight into its peers' mailboxes over NVLink peer memory by the gradient-reduction kernel itself, which
+  then sums the mailbox and applies Adam (include/surj_b200.h: surj_dp_create / surj_dp_connect /
+  surj_train_step_dp).  torch.distributed is only used once, to exchange the CUDA IPC handles."""
+
+  def __init__(self, n_params, group=None):
+    import ctypes as C
+
+    from surjectors_b200 import _abi
+
+    self._lib = _abi.lib()
+    self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+    handle = C.create_string_buffer(64)
+    self._h = C.c_void_p()
+    _abi.check(self._lib.surj_dp_create(self.rank, self.world, int(n_params), C.byref(self._h), handle), "surj_dp_create")
+    handles = [None] * self.world
+    dist.all_gather_object(handles, bytes(handle.raw), group=group)
+    _abi.check(self._lib.surj_dp_connect(self._h, b"".join(handles)), "surj_dp_connect")
+    dist.barrier(group=group)
+
+  @property
+  def handle(self):
+    return self._h
+
+  def error(self):
+    return int(self._lib.surj_dp_error(self._h))
+
+  def close(self):
+    if self._h:
+      self._lib.surj_dp_destroy(self._h)
+      self._h = None

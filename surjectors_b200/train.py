@@ -55,10 +55,18 @@ class TrainStep:
     self.reduction = reduction
     self.group = process_group
     self.world = 1
+    self.peer = None
     if process_group is not None:
+      import os
+
       import torch.distributed as dist
 
       self.world = dist.get_world_size(process_group)
+      # KB-sized gradients: exchange fused into the reduction kernel over NVLink peer memory; large ones
+      # (wide networks, per-op executor): one NCCL all-reduce.  SURJ_B200_EXCHANGE=nccl forces the latter.
+      if (self.world > 1 and self.plan.is_fused and self.flat.numel() <= (1 << 16)
+          and os.environ.get("SURJ_B200_EXCHANGE", "peer") != "nccl"):
+        self.peer = parallel.PeerExchange(self.flat.numel(), process_group)
 
   @property
   def loss(self):
@@ -66,7 +74,7 @@ class TrainStep:
     return self.grads[self.flat.numel():self.flat.numel() + 1]
 
   def launches_per_step(self):
-    if self.world == 1 and self.plan.is_fused:
+    if self.plan.is_fused and (self.world == 1 or self.peer is not None):
       return 2
     return self.plan.launches(backward=True) + 2 + (1 if self.world > 1 else 0)
 
@@ -77,6 +85,9 @@ class TrainStep:
     xx = x if self.plan.dim_x > 0 else None
     if self.world == 1:  # the whole step is two launches: backward kernel, reduction + Adam
       self.plan.train_step(y, xx, self.flat, g_scale, self.grads, self.opt, self.grads[n:n + 1])
+      return self.loss
+    if self.peer is not None:  # same two launches; the sum over ranks happens inside the reduction kernel
+      self.plan.train_step_dp(self.peer, y, xx, self.flat, g_scale, self.grads, self.opt, self.grads[n:n + 1])
       return self.loss
     self.plan.bwd(y, xx, self.flat, g_lp=None, g_scale=g_scale, g_params=self.grads, loss_out=self.grads[n:n + 1])
     if self.world > 1:
