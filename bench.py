@@ -284,10 +284,10 @@ def run_b200(args):
       torch.cuda.synchronize(dev)
       # keep the sampler alive for at least a few samples when the region is very short
       ms = e0.elapsed_time(e1)
-      if ms < 400.0:
+      if ms < 1000.0:
         # same load, outside the timed region, until nvidia-smi has a few samples; the number of extra
         # passes is agreed between ranks (every step contains a collective)
-        extra = int(max_over_ranks(400.0 / max(ms / args.steps, 1e-3) / P)) + 1
+        extra = int(max_over_ranks(1000.0 / max(ms / args.steps, 1e-3) / P)) + 1
         for _ in range(min(extra, 4096)):
           run_steps(P)
         torch.cuda.synchronize(dev)
@@ -342,6 +342,30 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     fp32_peak = 5 * fl.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
 
+  # --- the other half of BASELINE.json's metric: log_prob (inference) samples/s, same pool of resident batches
+  lp_buf = torch.empty(B, dtype=torch.float32, device=dev)
+  with torch.cuda.stream(stream):
+    def lp_pass():
+      for i in range(P):
+        ts.plan.fwd(dev_y[i], dev_x[i] if DX else None, ts.flat, want_z=False, lp_out=lp_buf)
+    lp_pass()
+    torch.cuda.synchronize(dev)
+    lg = None
+    if use_graph:
+      lg = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(lg, stream=stream):
+        lp_pass()
+      lg.replay()
+      torch.cuda.synchronize(dev)
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record(stream)
+    for _ in range(10):
+      lg.replay() if lg is not None else lp_pass()
+    l1.record(stream)
+    torch.cuda.synchronize(dev)
+    lp_ms = max_over_ranks(l0.elapsed_time(l1) / (10 * P))
+  logprob = {"samples_per_sec": world * B / (lp_ms * 1e-3), "us_per_call": 1e3 * lp_ms,
+             "api": "surj_chain_logprob_fwd (fused forward kernel), no collective"}
   _dbg("roofline done")
   need, dense = _cost.forward_flops(ts.spec)
   flops_launch = 3.0 * need * B
@@ -413,7 +437,7 @@ def run_b200(args):
                  "l2": f"pool of {P} distinct batches ({P * B * (D + DX) * 4 / 1e6:.0f} MB > 126 MB L2) cycled",
                  "cuda_graph": bool(use_graph), "train_steps_per_sec": args.steps / (ms * 1e-3)},
       "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps * ts.launches_per_step(),
-      "roofline": roofline, "cpu_baseline": cpu, "final_loss": loss_resident,
+      "roofline": roofline, "cpu_baseline": cpu, "log_prob": logprob, "final_loss": loss_resident,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
