@@ -166,11 +166,17 @@ int surj_adam_step(SurjStream stream, float* params, const float* grads, float* 
 
 /* --- sampling direction: Surjector.forward_and_likelihood_contribution through the chain in reverse
  * (surjectors/_src/surjectors/chain.py:47-67): y_out[B, dim_in] and the summed forward log-det
- * ld_out[B] for latents z[B, dim_out].  Implemented for chains of bijectors (MaskedCoupling,
- * MaskedAutoregressive -- its D-pass recursion masked_autoregressive.py:63-71 --, Permutation); returns
- * SURJ_E_UNSUPPORTED for LULinear (no forward upstream either, lu_linear.py:92-93) and for surjections. */
-int surj_chain_forward(const SurjPlan* plan, SurjStream stream, const float* z, const float* x, const float* params,
-                       float* y_out, float* ld_out, void* workspace, size_t workspace_bytes, int64_t batch);
+ * ld_out[B] for latents z[B, dim_out].  Implemented for MaskedCoupling, MaskedAutoregressive (its D-pass
+ * recursion, masked_autoregressive.py:63-71), Permutation, Slice (slice.py:70-78) and the coupling funnels
+ * (masked_coupling_inference_funnel.py:93-106); SURJ_E_UNSUPPORTED for LULinear (no forward upstream either,
+ * lu_linear.py:92-93) and the autoregressive funnels (broken upstream). */
+int surj_chain_forward(const SurjPlan* plan, SurjStream stream, const float* z, const float* x, const float* eps,
+                       const float* params, float* y_out, float* ld_out, void* workspace, size_t workspace_bytes,
+                       int64_t batch);
+/* standard-normal draws per sample that the sampling direction consumes (sum of the dropped widths of Slice /
+ * coupling funnels, assigned in sampling order: last layer first); eps[B, noise_dim] comes from the caller's RNG --
+ * the reference draws them with hk.next_rng_key() (slice.py:74-76), so a jax.ffi binding can pass its own stream */
+int32_t surj_plan_noise_dim(const SurjPlan* plan);
 size_t surj_plan_forward_workspace_bytes(const SurjPlan* plan, int64_t batch);
 
 /* --- one training step = the jitted `step` of examples/coupling_inference_surjection.py:81-90:

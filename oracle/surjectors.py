@@ -340,6 +340,17 @@ class Permutation(Bijector):
 
 
 # --------------------------------------------------------------- surjectors (a13-a15)
+noise_provider = None  # tests set this to fn(shape, dtype) -> standard-normal draws for decoder samples
+
+
+def _decoder_sample_and_log_prob(dist, like):
+  """distrax Independent(Normal).sample_and_log_prob: loc + scale * eps, and the log-prob of that sample."""
+  inner = dist.distribution
+  eps = noise_provider(tuple(inner.loc.shape), inner.loc.dtype)
+  sample = inner.loc + inner.scale * eps
+  return sample, dist.log_prob(sample)
+
+
 class Slice(Surjector):
   """_src/surjectors/slice.py:8-78."""
 
@@ -352,8 +363,10 @@ class Slice(Surjector):
     z_condition = z if x is None else torch.cat([z, x], dim=-1)
     return z, self.decoder(z_condition).log_prob(y_minus)
 
-  def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):
-    raise NotImplementedError("sampling direction is SURVEY section 8f (next)")
+  def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):  # slice.py:70-78
+    z_condition = z if x is None else torch.cat([z, x], dim=-1)
+    y_minus, lc = _decoder_sample_and_log_prob(self.decoder(z_condition), z)
+    return torch.cat([z, y_minus], dim=-1), lc
 
 
 class MaskedCouplingInferenceFunnel(Surjector):
@@ -376,8 +389,13 @@ class MaskedCouplingInferenceFunnel(Surjector):
     lc = self.decoder(z_condition).log_prob(y[:, self.n_keep :])
     return z, lc + jac_det
 
-  def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):
-    raise NotImplementedError("sampling direction is SURVEY section 8f (next)")
+  def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):  # :93-106
+    z_condition = z if x is None else torch.cat([z, x], dim=-1)
+    y_minus, jac_det = _decoder_sample_and_log_prob(self.decoder(z_condition), z)
+    z_tilde = torch.cat([z, y_minus], dim=-1)
+    inner = MaskedCoupling(self._mask(z_tilde), self.conditioner, self.bijector_fn)
+    y, lc = inner.forward_and_log_det(z_tilde, x)
+    return y, lc + jac_det
 
 
 class AffineMaskedCouplingInferenceFunnel(MaskedCouplingInferenceFunnel):

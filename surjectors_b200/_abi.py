@@ -101,7 +101,8 @@ _SIGNATURES = {
   "surj_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
   "surj_chain_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_size_t, C.c_int64]),
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
+  "surj_plan_noise_dim": (C.c_int32, [C.c_void_p]),
   "surj_plan_forward_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
   "surj_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,

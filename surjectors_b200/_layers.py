@@ -53,9 +53,9 @@ class Surjector:
     return _runtime.run_transform(self, y, x, honour_x=True)
 
   def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):
-    """Sampling direction: implemented for chains of bijectors -- MaskedCoupling,
-    MaskedAutoregressive (the D-pass recursion of masked_autoregressive.py:63-71), Permutation; the C ABI
-    reports NotImplementedError for LULinear (no forward upstream, lu_linear.py:92-93) and surjections."""
+    """Sampling direction: MaskedCoupling, MaskedAutoregressive (the D-pass recursion of
+    masked_autoregressive.py:63-71), Permutation, Slice and the coupling funnels (decoder samples from noise the
+    host draws); NotImplementedError for LULinear (no forward upstream, lu_linear.py:92-93) and the AR funnels."""
     from surjectors_b200 import _runtime
 
     return _runtime.run_forward(self, z, x, honour_x=True)
@@ -354,16 +354,33 @@ class AffineMaskedAutoregressiveInferenceFunnel(MaskedAutoregressiveInferenceFun
 
 
 # ----------------------------------------------------------------------- driver
-def input_dim_for_latent(transform, d_latent):
-  """Data-space width of a transform given its latent width (bijectors keep the width; a Chain of
-  bijectors too).  Dimension-reducing layers have no sampling direction here yet."""
+def _decoder_event_width(decoder, k, dx):
+  """Width of the variable a decoder scores / samples, read off its network: Independent(Normal(mu, sigma))
+  with (mu, log_sigma) = split(net([z, x]), 2, -1)."""
+  src = _sym.InputSym(k + dx)
+  dist = decoder(src)
+  inner = getattr(dist, "distribution", dist)
+  loc = getattr(inner, "loc", None)
+  if not isinstance(loc, _sym.SplitSym):
+    raise _sym.Unsupported("decoder must return Independent(Normal(mu, exp(log_sigma))) with (mu, log_sigma) = jnp.split(net(z), 2, -1)")
+  return int(loc.shape[-1])
+
+
+def input_dim_for_latent(transform, d_latent, dx=0):
+  """Data-space width of a transform given its latent width: bijectors keep the width, Slice / coupling funnels
+  add the width of what their decoder generates (the reference never needs this: its decoder output fixes it)."""
   layers = transform._transforms if isinstance(transform, Chain) else [transform]
-  for t in layers:
-    if isinstance(t, (Slice, MaskedCouplingInferenceFunnel, MaskedAutoregressiveInferenceFunnel)):
+  d = d_latent
+  for t in reversed(layers):
+    if isinstance(t, MaskedAutoregressiveInferenceFunnel):
       raise NotImplementedError(
-        f"{type(t).__name__}: sampling through dimension-reducing surjections (decoder sampling) is the next step "
-        "(SURVEY.md section 8f.1); log_prob and its gradient are implemented")
-  return d_latent
+        f"{type(t).__name__}: sampling through autoregressive funnels is broken upstream (it concatenates on the batch "
+        "axis, masked_autoregressive_inference_funnel.py:107) and is not provided; log_prob and its gradient are")
+    if isinstance(t, (Slice, MaskedCouplingInferenceFunnel)):
+      if d != t.n_keep:
+        raise ValueError(f"{type(t).__name__}(n_keep={t.n_keep}) cannot generate from a latent of {d} dims")
+      d = t.n_keep + _decoder_event_width(t.decoder, t.n_keep, dx)
+  return d
 
 
 def trace_chain(transform, d_in, dx, honour_x=True) -> ChainSpec:

@@ -121,8 +121,9 @@ class Plan:
     return gp, gy, gx, lp
 
 
-def _plan_forward(self, z, x, flat):
-  """surj_chain_forward: (y, summed forward log-det) for latents z (sampling direction)."""
+def _plan_forward(self, z, x, flat, eps=None):
+  """surj_chain_forward: (y, summed forward contribution) for latents z (sampling direction); eps[B, noise_dim]
+  are the standard-normal draws the decoders of Slice / funnel layers consume."""
   B = z.shape[0]
   if not z.is_cuda:
     raise _abi.SurjError("surjectors_b200 computes on CUDA tensors only (there is no CPU fallback)")
@@ -138,13 +139,18 @@ def _plan_forward(self, z, x, flat):
   if ws is None or ws.numel() < n:
     ws = torch.empty(max(n, 16), dtype=torch.uint8, device=z.device)
     self._ws[key] = ws
-  st = self._lib.surj_chain_forward(self._h, _stream(z), z.data_ptr(), _ptr(x), flat.data_ptr(), y.data_ptr(),
-                                    ld.data_ptr(), ws.data_ptr(), n, B)
+  n_eps = self.noise_dim()
+  if n_eps > 0 and (eps is None or tuple(eps.shape) != (B, n_eps) or eps.dtype != torch.float32 or not eps.is_contiguous()
+                    or eps.device != z.device):
+    raise ValueError(f"eps must be a contiguous float32 [B, {n_eps}] tensor on the device of z")
+  st = self._lib.surj_chain_forward(self._h, _stream(z), z.data_ptr(), _ptr(x), _ptr(eps) if n_eps else None,
+                                    flat.data_ptr(), y.data_ptr(), ld.data_ptr(), ws.data_ptr(), n, B)
   _abi.check(st, "surj_chain_forward")
   return y, ld
 
 
 Plan.forward = _plan_forward
+Plan.noise_dim = lambda self: int(self._lib.surj_plan_noise_dim(self._h))
 
 
 def _plan_train_step(self, y, x, flat, g_scale, grads, opt, loss_out):
@@ -271,9 +277,10 @@ def run_transform(transform, y, x, honour_x=True, base=None):
   return plan.fwd(y, xx, flat, want_z=True)
 
 
-def run_forward(transform, z, x, honour_x=True):
+def run_forward(transform, z, x, honour_x=True, eps=None):
   """Sampling direction: trace `transform` (its structure is direction-independent) and run
-  forward_and_likelihood_contribution: returns (y, forward log-det)."""
+  forward_and_likelihood_contribution: returns (y, forward contribution).  Decoder noise `eps` defaults to
+  standard-normal draws from the haiku rng of this apply (the reference draws with hk.next_rng_key())."""
   from surjectors_b200 import _layers
 
   fr = hk.current_frame()
@@ -282,7 +289,7 @@ def run_forward(transform, z, x, honour_x=True):
   if z.dim() != 2:
     raise ValueError(f"z must have shape [batch, event], got {tuple(z.shape)}")
   dx = x.shape[-1] if (x is not None and honour_x) else 0
-  d_in = _layers.input_dim_for_latent(transform, z.shape[-1])
+  d_in = _layers.input_dim_for_latent(transform, z.shape[-1], dx)
   spec = _layers.trace_chain(transform, d_in, dx)
   if spec.dim_out != z.shape[-1]:
     raise ValueError(f"latent has {z.shape[-1]} dims but the flow's latent space has {spec.dim_out}")
@@ -293,7 +300,14 @@ def run_forward(transform, z, x, honour_x=True):
             torch.zeros(B, dtype=torch.float32, device=z.device))
   plan = get_plan(spec, BASE_NONE)
   flat = hk.pack_params(fr.params, fr.layout, z.device)
-  return plan.forward(z, x if dx > 0 else None, flat)
+  n_eps = plan.noise_dim()
+  if n_eps > 0 and eps is None:
+    rng = hk.next_rng_key()
+    if rng is None:
+      raise ValueError("sampling through a surjection draws decoder noise: pass an rng to apply")
+    g = torch.Generator(device="cpu").manual_seed(int(rng.integers(0, 2**62)))
+    eps = torch.randn((z.shape[0], n_eps), generator=g, dtype=torch.float32).to(z.device)
+  return plan.forward(z, x if dx > 0 else None, flat, _prep(eps, "eps") if n_eps else None)
 
 
 def value_and_grad(fun, has_aux=False):

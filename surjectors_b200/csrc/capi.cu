@@ -673,8 +673,10 @@ extern "C" int surj_train_step(const SurjPlan* plan, SurjStream stream, const fl
 // Sampling direction: Surjector.forward_and_likelihood_contribution through the Chain in reverse
 // (surjectors/_src/surjectors/chain.py:47-54).  Always runs on the chain program (the generated kernels
 // only cover log_prob and its VJP): fused interpreter kernel when it fits, else the per-op executor.
+extern "C" int32_t surj_plan_noise_dim(const SurjPlan* plan) { return plan && plan->vmp ? plan->vmp->n_eps : 0; }
+
 extern "C" int surj_chain_forward(const SurjPlan* plan, SurjStream stream, const float* z, const float* x,
-                                  const float* params, float* y_out, float* ld_out, void* workspace,
+                                  const float* eps, const float* params, float* y_out, float* ld_out, void* workspace,
                                   size_t workspace_bytes, int64_t batch) {
   int r = check_io(plan, z, x, params, batch);
   if (r) return r;
@@ -686,14 +688,18 @@ extern "C" int surj_chain_forward(const SurjPlan* plan, SurjStream stream, const
     surj_set_error(plan->vmp ? plan->vmp->gen_why : std::string("chain has no program"));
     return SURJ_E_UNSUPPORTED;
   }
+  if (plan->vmp->n_eps > 0 && !eps) {
+    surj_set_error("this chain samples decoder distributions: eps[B, surj_plan_noise_dim] is required");
+    return SURJ_E_INVALID;
+  }
   r = vm_prepare(plan->vmp);
   if (r) return r;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->vmp->fused_ok && plan->mode != SURJ_MODE_LAYERED)
     return vm_launch(plan->vmp, st, VM_PROG_GEN, 0, z, x, params, nullptr, 0.0f, nullptr, y_out, ld_out, nullptr, nullptr,
-                     nullptr, 0, batch, vm_grid(plan->vmp, batch, VM_PROG_GEN), nullptr, 0);
+                     nullptr, 0, batch, vm_grid(plan->vmp, batch, VM_PROG_GEN), nullptr, 0, eps);
   return vm_global_run(plan->vmp, st, VM_PROG_GEN, 0, z, x, params, nullptr, 0.0f, nullptr, y_out, ld_out, nullptr, nullptr,
-                       nullptr, nullptr, workspace, workspace_bytes, batch);
+                       nullptr, nullptr, workspace, workspace_bytes, batch, eps);
 }
 
 extern "C" size_t surj_plan_forward_workspace_bytes(const SurjPlan* plan, int64_t batch) {

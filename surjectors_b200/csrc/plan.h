@@ -37,4 +37,4 @@ int vm_max_grid(const struct VmPlan* v, int64_t B);
 int vm_launch(struct VmPlan* v, cudaStream_t st, int prog, int with_base, const float* y, const float* x,
               const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
               float* g_y, float* g_x, float* partials, int npad, int64_t B, int grid, unsigned* tickets,
-              int n_tickets);
+              int n_tickets, const float* eps = nullptr);

@@ -65,7 +65,8 @@ enum : int32_t {
   OP_LINEAR_DW,     // a0 in_row, a1 n_in, a2 g_row, a3 n_out_pad, a4 w_off, a5 ld, a6 b_off
                     // (the input-gradient matvec g_in = g W^T is an OP_LINEAR on the transposed copy of W)
   OP_SCALAR_BWD,    // a0 scalar slot : slot += sum over the tile of g_lp
-  OP_LOAD_GLP       // (backward) g_lp registers <- g_lp[s] or g_scale
+  OP_NORMAL_SAMPLE  // a0 out_row, a1 n_v, a2 mu_row, a3 ls_row, a4 eps_col : out = mu + exp(ls) * eps[:, eps_col + j];
+                    // lp += log N(out; mu, exp(ls))   (decoder sample_and_log_prob, slice.py:74-76)
 };
 
 enum : int { ACT_IDENTITY = 0, ACT_RELU = 1, ACT_SWISH = 2, ACT_TANH = 3, ACT_SIGMOID = 4, ACT_SOFTPLUS = 5,

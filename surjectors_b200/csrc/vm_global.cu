@@ -272,7 +272,8 @@ int vm_global_launches(const VmPlan* v, int64_t B, bool backward) {
 
 int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const float* y, const float* x,
                   const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
-                  float* g_y, float* g_x, float* g_params, float* loss_out, void* ws, size_t ws_bytes, int64_t B) {
+                  float* g_y, float* g_x, float* g_params, float* loss_out, void* ws, size_t ws_bytes, int64_t B,
+                  const float* eps) {
   const bool backward = prog == VM_PROG_BWD;
   const int C = chunk_cols(B, v->n_rows);
   Carve k = carve(v, ws, C, backward);
@@ -300,6 +301,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   vm::Io io;
   io.y = y; io.x = x; io.g_lp = g_lp; io.g_z = g_z; io.z_out = z_out; io.lp_out = lp_out; io.g_y = g_y; io.g_x = g_x;
   io.g_scale = g_scale; io.with_base = with_base; io.backward = backward ? 1 : 0;
+  io.eps = eps; io.n_eps = v->n_eps;
 
   vm::vg_stage<<<std::min((n_par + 255) / 256, 148 * 8), 256, 0, st>>>(P.stage, n_par, params, k.par, k.grad, backward ? 1 : 0,
                                                                       k.scal_g, v->n_scalars, k.loss);

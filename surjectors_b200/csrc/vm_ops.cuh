@@ -12,6 +12,7 @@ enum : int { ROW_ONES = 0, ROW_LP = 1, ROW_GLP = 2, ROW_FIRST_FREE = 3 };
 
 struct Io {  // caller buffers of one C-ABI call
   const float* y; const float* x; const float* g_lp; const float* g_z;
+  const float* eps; int n_eps;  // sampling direction: standard-normal draws [B, n_eps] supplied by the caller
   float* z_out; float* lp_out; float* g_y; float* g_x;
   float g_scale; int with_base; int backward;
 };
@@ -251,6 +252,17 @@ VM_DEV bool exec_simple(Ctx<NT, S>& c, const Op& op, const Io& io, float& lp_tot
     case OP_AFFINE: op_affine<NT, S>(c, op); return true;
     case OP_RQS: op_rqs<NT, S>(c, op); return true;
     case OP_NORMAL_LP: op_normal_lp<NT, S>(c, op); return true;
+    case OP_NORMAL_SAMPLE:
+      for (int j = 0; j < op.a[1]; ++j)
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const long long g = c.sample(s);
+          const float e = g < c.B ? __ldg(io.eps + g * io.n_eps + op.a[4] + j) : 0.0f;
+          const float l = c.row(op.a[3] + j)[s * NT];
+          c.row(op.a[0] + j)[s * NT] = fmaf(expf(l), e, c.row(op.a[2] + j)[s * NT]);
+          c.lp[s] += -0.5f * e * e - l - VM_HALF_LOG_2PI;
+        }
+      return true;
     case OP_ADD_SCALAR:
 #pragma unroll
       for (int s = 0; s < S; ++s) c.lp[s] += c.scal[op.a[0]];

@@ -260,6 +260,15 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
   B.scratch_base = B.scratch_top = B.rows_next;
 
   std::vector<LayerCode> code(L);
+  int n_eps = 0;  // noise columns are assigned in sampling order (last layer first)
+  std::vector<int> eps_col(L, -1);
+  for (int l = L - 1; l >= 0; --l) {
+    const SurjLayerDesc& Ld = plan->layers[l];
+    if (Ld.kind == SURJ_LAYER_SLICE || Ld.kind == SURJ_LAYER_COUPLING_FUNNEL) {
+      eps_col[l] = n_eps;
+      n_eps += Ld.dim_in - Ld.dim_out;
+    }
+  }
   for (int l = 0; l < L; ++l) {
     const SurjLayerDesc& Ld = plan->layers[l];
     LayerCode& C = code[l];
@@ -352,6 +361,22 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
             const int thd = drows.back().post_row;
             C.fwd.push_back(mk(vm::OP_NORMAL_LP, {Ein + K, nv, thd, thd + nv}));
           }
+        }
+        if (funnel) {  // sampling direction (masked_coupling_inference_funnel.py:93-106): y- ~ decoder([z, x]), then the
+                       // coupling forward of z conditioned on the sampled y- (+ x)
+          B.scratch_reset();
+          std::vector<NetRows> drows;
+          int c_row;
+          emit_dec_fwd(C.gen, false, drows, c_row);
+          const int thd = drows.back().post_row;
+          C.gen.push_back(mk(vm::OP_NORMAL_SAMPLE, {Ein + K, nv, thd, thd + nv, eps_col[l]}));
+          const int m_row = B.scratch(pad8(cin));
+          C.gen.push_back(mk(vm::OP_GATHER, {m_row, cin, B.tab(msrc)}));  // [y[K:], x]: rows of E[l] just written
+          std::vector<NetRows> rows = emit_mlp_fwd(B, C.gen, mats, Ld.conditioner.act, m_row, false);
+          const int th = rows.back().post_row;
+          if (rqs) C.gen.push_back(mk(vm::OP_RQS, {Eout, Ein, n_t, t_dims, th, Kb, Ld.inner ^ 1, 0}, lo, hi));
+          else C.gen.push_back(mk(vm::OP_AFFINE, {Eout, Ein, n_t, t_dims, th, 1, th + n_t, 1, Ld.inner ^ 1, 0}));
+          C.gen_ok = true;
         }
         if (!funnel) {  // sampling direction (masked_coupling.py:59-71): same conditioner on the pass-through dims of z,
                         // inner bijector in the other direction (inner ^ 1 swaps X <-> Inverse(X))
@@ -523,6 +548,15 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
           C.bwd.push_back(mk(vm::OP_ADD, {Gin, c_row, K}));
           if (dxu) C.bwd.push_back(mk(vm::OP_ADD, {GX, c_row + K, dxu}));
         }
+        {  // sampling direction (slice.py:70-78): y = [z, y-] with y- ~ decoder([z, x]); contribution = log p(y- | z)
+          B.scratch_reset();
+          std::vector<NetRows> drows;
+          int c_row;
+          emit_dec_fwd(C.gen, false, drows, c_row);  // z already sits in the first K rows (E[l+1] aliases E[l])
+          const int thd = drows.back().post_row;
+          C.gen.push_back(mk(vm::OP_NORMAL_SAMPLE, {Ein + K, nv, thd, thd + nv, eps_col[l]}));
+          C.gen_ok = true;
+        }
         break;
       }
       case SURJ_LAYER_LU: {
@@ -623,6 +657,7 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
   while (B.stage.size() & 3) B.push(vm::STAGE_ZERO, -1);
   v->stage = B.stage; v->grad_dst = B.grad_dst; v->grad_aux = B.grad_aux; v->itab = B.itab; v->sjobs = B.sjobs;
   v->n_scalars = B.n_scalars;
+  v->n_eps = n_eps;
   v->n_rows = B.scratch_base + (B.scratch_max - B.scratch_base);
   v->d_in = plan->dim_in; v->d_x = dx; v->d_out = dz; v->n_params = (int)plan->n_params;
 
@@ -738,7 +773,7 @@ int vm_max_grid(const VmPlan* v, int64_t B) {  // upper bound usable before a de
 int vm_launch(VmPlan* v, cudaStream_t st, int prog, int with_base, const float* y, const float* x,
               const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
               float* g_y, float* g_x, float* partials, int npad, int64_t B, int grid, unsigned* tickets,
-              int n_tickets) {
+              int n_tickets, const float* eps) {
   const bool backward = prog == VM_PROG_BWD;
   vm::Program P = v->prog;
   P.ops = backward ? v->d_ops_bwd : (prog == VM_PROG_GEN ? v->d_ops_gen : v->d_ops_fwd);
@@ -746,6 +781,7 @@ int vm_launch(VmPlan* v, cudaStream_t st, int prog, int with_base, const float* 
   vm::Io io;
   io.y = y; io.x = x; io.g_lp = g_lp; io.g_z = g_z; io.z_out = z_out; io.lp_out = lp_out; io.g_y = g_y; io.g_x = g_x;
   io.g_scale = g_scale; io.with_base = with_base; io.backward = backward ? 1 : 0;
+  io.eps = eps; io.n_eps = v->n_eps;
   VmKernel k = vm_kernel_for(v->nt, v->s);
   k<<<grid, v->nt, backward ? v->smem_bwd : (prog == VM_PROG_GEN ? v->smem_gen : v->smem_fwd), st>>>(P, io, params, partials, npad, (long long)B, tickets,
                                                                 n_tickets);

@@ -9,6 +9,7 @@
 struct VmPlan {
   std::vector<vm::Op> ops_fwd, ops_bwd, ops_gen;  // log_prob, its VJP, sampling direction (empty: unsupported)
   std::string gen_why;
+  int n_eps = 0;  // standard-normal draws per sample the sampling direction consumes (decoder samples)
   std::vector<int32_t> stage, grad_dst, grad_aux, itab;
   std::vector<vm::ScalarJob> sjobs;
   int n_scalars = 0, n_rows = 0;
@@ -34,4 +35,5 @@ size_t vm_global_workspace_bytes(const VmPlan* v, int64_t B, bool backward);
 int vm_global_launches(const VmPlan* v, int64_t B, bool backward);
 int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const float* y, const float* x,
                   const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
-                  float* g_y, float* g_x, float* g_params, float* loss_out, void* ws, size_t ws_bytes, int64_t B);
+                  float* g_y, float* g_x, float* g_params, float* loss_out, void* ws, size_t ws_bytes, int64_t B,
+                  const float* eps = nullptr);

@@ -132,3 +132,71 @@ def test_lulinear_and_surjections_have_no_sampling_direction():
   params = m.init(0, z=z)
   with pytest.raises(NotImplementedError):  # lu_linear.py:92-93 raises upstream as well
     m.apply(params, None, z=z)
+
+
+@pytest.mark.parametrize("mode", ["fused", "layered"])
+@pytest.mark.parametrize("name", ["cfg2", "cfg4"])
+def test_sampling_through_surjections_matches_oracle(name, mode):
+  """Slice / coupling-funnel sampling (slice.py:70-78, masked_coupling_inference_funnel.py:93-106) with the
+  decoder noise passed in explicitly: same z, same eps -> same y and same contribution as the oracle."""
+  from oracle import surjectors as OS
+  from oracle import hk as ohk
+  from oracle import configs as ocfg
+  from surjectors_b200 import _runtime, configs as pcfg, fused_chains
+  from tests import parity
+
+  scale = parity.SMALL.get(name, {})
+  pm, pparams, om, oparams, y64, x64 = parity.build_pair(name, 4, 0, 0.3, **scale)
+  c = pcfg.CONFIGS[name]
+  dim = scale.get("dim", c["dim"])
+  spec = fused_chains.spec_of(c["make"](**scale), dim, c["dim_x"])
+  B = 257
+  g = torch.Generator().manual_seed(2)
+  with execution_mode(mode):
+    plan = _runtime.get_plan(spec, _runtime.BASE_NONE)
+    n_eps, dz = plan.noise_dim(), plan.dim_out
+    assert n_eps > 0
+    z = torch.randn((B, dz), generator=g, dtype=torch.float64)
+    eps = torch.randn((B, n_eps), generator=g, dtype=torch.float64)
+    flat = parity.to_device(pparams, torch.device(DEV)).flat
+    y, fl = plan.forward(z.float().to(DEV).contiguous(), None, flat, eps.float().to(DEV).contiguous())
+  # oracle: same chain object, forward direction, noise handed out in the order the layers ask for it
+  cursor = {"k": 0}
+
+  def provider(shape, dtype):
+    n = shape[-1]
+    out = eps[:, cursor["k"] : cursor["k"] + n].to(dtype)
+    cursor["k"] += n
+    return out
+
+  chain_holder = {}
+  orig_td = OS.TransformedDistribution
+
+  class Capture(orig_td):
+    def log_prob(self, yy, xx=None):
+      chain_holder["y"], chain_holder["ld"] = self.transform.forward_and_likelihood_contribution(z, xx)
+      return torch.zeros(yy.shape[0], dtype=yy.dtype)
+
+  OS.TransformedDistribution = Capture
+  OS.noise_provider = provider
+  try:
+    om.apply(oparams, y=y64)
+  finally:
+    OS.TransformedDistribution = orig_td
+    OS.noise_provider = None
+  assert cursor["k"] == n_eps
+  yo, lo = chain_holder["y"], chain_holder["ld"]
+  assert torch.allclose(y.cpu().double(), yo, rtol=2e-5, atol=2e-5), float((y.cpu().double() - yo).abs().max())
+  assert parity.lp_error(fl.cpu().numpy(), lo.numpy()) <= 2e-5
+
+
+def test_sample_api_on_cfg2():
+  from surjectors_b200 import configs as pcfg
+
+  m = hk.transform(pcfg.CONFIGS["cfg2"]["make"]())
+  y0 = torch.zeros((4, 20), device=DEV)
+  params = m.init(3, method="log_prob", y=y0)
+  y, lp = m.apply(params, 11, method="sample_and_log_prob", sample_shape=(1000,))
+  assert tuple(y.shape) == (1000, 20) and tuple(lp.shape) == (1000,) and bool(torch.isfinite(y).all())
+  y2 = m.apply(params, 11, method="sample", sample_shape=(1000,))
+  assert torch.equal(y, y2)  # same rng -> same draws

@@ -183,7 +183,7 @@ def test_no_cpu_fallback():
   params = m.init(0, method="log_prob", y=y)
   with pytest.raises(_abi.SurjError, match="no CPU fallback"):
     m.apply(params, None, method="log_prob", y=y)
-  with pytest.raises(NotImplementedError):  # sampling through a surjection (decoder sampling) is section 8f, next
+  with pytest.raises(_abi.SurjError, match="no CPU fallback"):  # the sampling direction has no CPU path either
     m.apply(params, 0, method="sample", sample_shape=(2,))
 
 
