@@ -47,7 +47,9 @@ enum SurjLayerKind {
   SURJ_LAYER_MAF_FUNNEL = 3,      /* MaskedAutoregressiveInferenceFunnel _src/surjectors/masked_autoregressive_inference_funnel.py:77-90 */
   SURJ_LAYER_SLICE = 4,           /* Slice                          _src/surjectors/slice.py:58-68 */
   SURJ_LAYER_LU = 5,              /* LULinear                       _src/bijectors/lu_linear.py:68-90 */
-  SURJ_LAYER_PERMUTATION = 6      /* Permutation                    _src/bijectors/permutation.py:30-37 */
+  SURJ_LAYER_PERMUTATION = 6,     /* Permutation                    _src/bijectors/permutation.py:30-37 */
+  SURJ_LAYER_MLP_FUNNEL = 7       /* MLPInferenceFunnel             _src/surjectors/mlp.py:40-56: z = LULinear(y+) + Linear(y-);
+                                     lu_* offsets = its LULinear, conditioner = the one hk.Linear [D-K -> K], decoder sees z only */
 };
 
 /* Inner bijector returned by the user's bijector_fn (distrax semantics). */

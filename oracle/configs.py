@@ -143,6 +143,17 @@ def make_cfg5(dim=128, hidden=(512, 512), n_layers=16):
   return flow
 
 
+def make_mlpf(dim=20, n_keep=10, dec_hidden=(8, 8), n_lu=2):
+  def flow(y, x=None):
+    layers = [S.LULinear(dim) for _ in range(n_lu)]
+    layers.append(S.MLPInferenceFunnel(n_keep, _dec(dim - n_keep, dec_hidden)))
+    layers += [S.LULinear(n_keep) for _ in range(n_lu)]
+    td = S.TransformedDistribution(S.standard_normal_base(n_keep, y.dtype), S.Chain(layers))
+    return td.log_prob(y, x)
+
+  return flow
+
+
 def randomize(params, seed, w_std=0.3, b_val=None, b_std=0.1):
   """Replace haiku-default inits by non-trivial values so every transform is exercised
   (mirrors masked_coupling_test.py:78-82: TruncatedNormal(1.0) weights, ones bias)."""

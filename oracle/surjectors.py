@@ -369,6 +369,28 @@ class Slice(Surjector):
     return torch.cat([z, y_minus], dim=-1), lc
 
 
+class MLPInferenceFunnel(Surjector, hk.Module):
+  """_src/surjectors/mlp.py:10-59."""
+
+  def __init__(self, n_keep, decoder):
+    hk.Module.__init__(self)
+    self._r = LULinear(n_keep, False)
+    self._w_prime = hk.Linear(n_keep, True)
+    self.decoder = decoder
+    self.n_keep = n_keep
+
+  @hk._scoped
+  def _inverse_and_likelihood_contribution(self, y, x=None, **kwargs):  # :47-56
+    y_plus, y_minus = split(y, [self.n_keep], -1)
+    z, jac_det = self._r.inverse_and_likelihood_contribution(y_plus)
+    z = z + self._w_prime(y_minus)
+    lp = self.decoder(z).log_prob(y_minus)
+    return z, lp + jac_det
+
+  def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):  # :58-59
+    raise NotImplementedError()
+
+
 class MaskedCouplingInferenceFunnel(Surjector):
   """_src/surjectors/masked_coupling_inference_funnel.py:9-106."""
 

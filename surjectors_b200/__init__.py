@@ -18,6 +18,7 @@ from surjectors_b200._layers import (  # noqa: F401
   Bijector,
   Chain,
   LULinear,
+  MLPInferenceFunnel,
   MaskedAutoregressive,
   MaskedAutoregressiveInferenceFunnel,
   MaskedCoupling,
@@ -47,6 +48,7 @@ __all__ = [
   "AffineMaskedCouplingInferenceFunnel",
   "RationalQuadraticSplineMaskedCouplingInferenceFunnel",
   "LULinear",
+  "MLPInferenceFunnel",
   "Slice",
   "ScalarAffine",
   "RationalQuadraticSpline",

@@ -17,7 +17,8 @@ KEYLIB_PATH = os.path.join(LIB_DIR, "_surjkey.so")
 MAX_NET_LAYERS = 8
 
 # enums (include/surj_b200.h)
-LAYER_COUPLING, LAYER_COUPLING_FUNNEL, LAYER_MAF, LAYER_MAF_FUNNEL, LAYER_SLICE, LAYER_LU, LAYER_PERMUTATION = range(7)
+LAYER_COUPLING, LAYER_COUPLING_FUNNEL, LAYER_MAF, LAYER_MAF_FUNNEL, LAYER_SLICE, LAYER_LU, LAYER_PERMUTATION, \
+  LAYER_MLP_FUNNEL = range(8)
 INNER_AFFINE, INNER_AFFINE_INV, INNER_RQS, INNER_RQS_INV = range(4)
 LAYOUT_SPLIT, LAYOUT_INTERLEAVED = range(2)
 ACT = {

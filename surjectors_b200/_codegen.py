@@ -139,6 +139,8 @@ def _layer(L: LayerSpec, dx: int):
     inv = np.zeros(D, dtype=np.int32)
     inv[np.asarray(L.permutation)] = np.arange(D, dtype=np.int32)  # permutation.py:31-36
     return f"surj::PermL<{dx}, {', '.join(str(int(v)) for v in inv)}>"
+  if L.kind == _abi.LAYER_MLP_FUNNEL:
+    raise NotFusable("MLPInferenceFunnel runs on the chain program executors")
   raise NotFusable(f"unknown layer kind {L.kind}")
 
 

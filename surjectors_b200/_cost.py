@@ -63,6 +63,11 @@ def forward_flops(spec):
     if L.kind == _abi.LAYER_LU:
       need += 2 * D * D
       dense += 4 * D * D
+    if L.kind == _abi.LAYER_MLP_FUNNEL:
+      n, d = _mlp(L.conditioner)
+      need, dense = need + n + 2 * K * K, dense + d + 4 * K * K
+      n, d = _mlp(L.decoder)
+      need, dense = need + n, dense + d
   return need, dense
 
 

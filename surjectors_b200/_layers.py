@@ -276,6 +276,35 @@ class Slice(Surjector):
     return [spec], k
 
 
+class MLPInferenceFunnel(Surjector, hk.Module):
+  """surjectors/_src/surjectors/mlp.py:10-59: z = LULinear(y+) + hk.Linear(y-); lc = decoder(z).log_prob(y-) + log|det|.
+  The decoder sees z only (no x), exactly as upstream (:53); the forward direction raises upstream too (:58-59)."""
+
+  def __init__(self, n_keep, decoder):
+    hk.Module.__init__(self)
+    self._r = LULinear(n_keep, False)
+    self._w_prime = hk.Linear(n_keep, True)
+    self.decoder = decoder
+    self.n_keep = int(n_keep)
+
+  def _trace(self, d_in, dx):
+    k = self.n_keep
+    if not 0 < k < d_in:
+      raise ValueError(f"n_keep={k} must be in (0, {d_in})")
+    fr = hk.current_frame()
+    fr.module_stack.append((self, "__call__"))
+    try:
+      wp = self._w_prime(_sym.InputSym(d_in - k))
+    finally:
+      fr.module_stack.pop()
+    spec = LayerSpec(kind=_abi.LAYER_MLP_FUNNEL, dim_in=d_in, dim_out=k, use_x=False, conditioner=_mlp_spec(wp),
+                     decoder=_trace_decoder(self.decoder, k, 0, d_in - k), lu=(self._r._lower, self._r._upper, self._r._diag))
+    return [spec], k
+
+  def _forward_and_likelihood_contribution(self, z, x=None, **kwargs):
+    raise NotImplementedError()
+
+
 class MaskedCouplingInferenceFunnel(Surjector):
   """surjectors/_src/surjectors/masked_coupling_inference_funnel.py:9-106."""
 
@@ -376,6 +405,8 @@ def input_dim_for_latent(transform, d_latent, dx=0):
       raise NotImplementedError(
         f"{type(t).__name__}: sampling through autoregressive funnels is broken upstream (it concatenates on the batch "
         "axis, masked_autoregressive_inference_funnel.py:107) and is not provided; log_prob and its gradient are")
+    if isinstance(t, MLPInferenceFunnel):
+      raise NotImplementedError()  # mlp.py:58-59
     if isinstance(t, (Slice, MaskedCouplingInferenceFunnel)):
       if d != t.n_keep:
         raise ValueError(f"{type(t).__name__}(n_keep={t.n_keep}) cannot generate from a latent of {d} dims")

@@ -18,6 +18,7 @@ from surjectors_b200 import (
   AffineMaskedCouplingInferenceFunnel,
   Chain,
   LULinear,
+  MLPInferenceFunnel,
   MaskedAutoregressive,
   MaskedCoupling,
   Permutation,
@@ -159,10 +160,23 @@ def make_cfg5(dim=128, hidden=(512, 512), n_layers=16):
   return flow
 
 
+def make_mlpf(dim=20, n_keep=10, dec_hidden=(8, 8), n_lu=2):
+  """docs/notebooks/dimension_reduction.ipynb:397-420: LULinear layers around an MLPInferenceFunnel (section 8f.3)."""
+
+  def flow(method, **kwargs):
+    layers = [LULinear(dim) for _ in range(n_lu)]
+    layers.append(MLPInferenceFunnel(n_keep, _decoder_fn(dim - n_keep, dec_hidden)))
+    layers += [LULinear(n_keep) for _ in range(n_lu)]
+    return TransformedDistribution(_base(n_keep), Chain(layers))(method=method, **kwargs)
+
+  return flow
+
+
 CONFIGS = {
   "cfg1": dict(make=make_cfg1, dim=10, dim_x=0, batch=4096),
   "cfg2": dict(make=make_cfg2, dim=20, dim_x=0, batch=65536),
   "cfg3": dict(make=make_cfg3, dim=20, dim_x=0, batch=65536),
   "cfg4": dict(make=make_cfg4, dim=64, dim_x=0, batch=1 << 20),
   "cfg5": dict(make=make_cfg5, dim=128, dim_x=16, batch=1 << 23),
+  "mlpf": dict(make=make_mlpf, dim=20, dim_x=0, batch=65536),
 }

@@ -181,15 +181,17 @@ static int validate_layer(const SurjLayerDesc& L, int k, int d_in, int dim_x, in
     return SURJ_E_INVALID;
   }
   const int dx = L.use_x ? dim_x : 0;
-  const bool funnel =
-      L.kind == SURJ_LAYER_COUPLING_FUNNEL || L.kind == SURJ_LAYER_MAF_FUNNEL || L.kind == SURJ_LAYER_SLICE;
+  const bool funnel = L.kind == SURJ_LAYER_COUPLING_FUNNEL || L.kind == SURJ_LAYER_MAF_FUNNEL ||
+                      L.kind == SURJ_LAYER_SLICE || L.kind == SURJ_LAYER_MLP_FUNNEL;
   if (funnel) {
     if (L.dim_out <= 0 || L.dim_out >= L.dim_in) {
       snprintf(buf, sizeof buf, "%s: n_keep=%d must be in (0, %d)", what, L.dim_out, L.dim_in);
       surj_set_error(buf);
       return SURJ_E_INVALID;
     }
-    int r = check_mlp(L.decoder, L.dim_out + dx, 2 * (L.dim_in - L.dim_out), np, "decoder");
+    // the MLP funnel's decoder sees z only (mlp.py:53), the others [z, x]
+    int r = check_mlp(L.decoder, L.dim_out + (L.kind == SURJ_LAYER_MLP_FUNNEL ? 0 : dx), 2 * (L.dim_in - L.dim_out), np,
+                      "decoder");
     if (r) return r;
   } else if (L.dim_out != L.dim_in) {
     surj_set_error(std::string(what) + ": bijector must keep the width");
@@ -225,6 +227,19 @@ static int validate_layer(const SurjLayerDesc& L, int k, int d_in, int dim_x, in
       return check_made(L.made, L.dim_out, inner_params(L), L.dim_in - L.dim_out + dx, np, "MADE");
     case SURJ_LAYER_SLICE:
       return SURJ_OK;
+    case SURJ_LAYER_MLP_FUNNEL: {
+      const int64_t n = L.dim_out, tri = n * (n - 1) / 2;
+      if (L.lu_lower_off < 0 || L.lu_lower_off + tri > np || L.lu_upper_off < 0 || L.lu_upper_off + tri > np ||
+          L.lu_diag_off < 0 || L.lu_diag_off + n > np) {
+        surj_set_error(std::string(what) + ": LULinear offsets out of range");
+        return SURJ_E_INVALID;
+      }
+      if (L.conditioner.n_layers != 1) {
+        surj_set_error(std::string(what) + ": the y- path of an MLP funnel is ONE hk.Linear");
+        return SURJ_E_INVALID;
+      }
+      return check_mlp(L.conditioner, L.dim_in - L.dim_out, L.dim_out, np, "w_prime");
+    }
     case SURJ_LAYER_LU: {
       const int64_t n = L.dim_in, tri = n * (n - 1) / 2;
       if (L.lu_lower_off < 0 || L.lu_lower_off + tri > np || L.lu_upper_off < 0 || L.lu_upper_off + tri > np ||

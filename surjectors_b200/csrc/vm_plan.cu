@@ -297,14 +297,15 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
     // decoder shared by SLICE / funnels: c = [z, x] -> Linear stack -> (mu | log_sigma)
     std::vector<Mat> dec_mats;
     const bool has_dec = Ld.kind == SURJ_LAYER_SLICE || Ld.kind == SURJ_LAYER_COUPLING_FUNNEL ||
-                         Ld.kind == SURJ_LAYER_MAF_FUNNEL;
+                         Ld.kind == SURJ_LAYER_MAF_FUNNEL || Ld.kind == SURJ_LAYER_MLP_FUNNEL;
     if (has_dec) dec_mats = build_mlp(B, Ld.decoder, nullptr, nullptr);
     const int nv = D - K;
     auto emit_dec_fwd = [&](std::vector<Op>& ops, bool train, std::vector<NetRows>& rows, int& c_row) {
-      const int cin = K + dxu;
+      const int dec_x = Ld.kind == SURJ_LAYER_MLP_FUNNEL ? 0 : dxu;  // mlp.py:53: decoder(z), no x
+      const int cin = K + dec_x;
       c_row = B.scratch(pad8(cin));
       std::vector<int> src = iota(K, Eout);
-      xrows(src);
+      if (dec_x) xrows(src);
       ops.push_back(mk(vm::OP_GATHER, {c_row, cin, B.tab(src)}));
       rows = emit_mlp_fwd(B, ops, dec_mats, Ld.decoder.act, c_row, train);
     };
@@ -556,6 +557,61 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
           const int thd = drows.back().post_row;
           C.gen.push_back(mk(vm::OP_NORMAL_SAMPLE, {Ein + K, nv, thd, thd + nv, eps_col[l]}));
           C.gen_ok = true;
+        }
+        break;
+      }
+      case SURJ_LAYER_MLP_FUNNEL: {
+        // mlp.py:47-56: z = LULinear(y+) + Linear(y-); lc = decoder(z).log_prob(y-) + log|det|
+        const int n = K;
+        const int slot = B.n_scalars++;
+        const int64_t lo_ = Ld.lu_lower_off, up_ = Ld.lu_upper_off, dg_ = Ld.lu_diag_off;
+        auto usrc = [&](int r, int c) -> Builder::Ent {
+          if (r < c) { const int p = (int)(up_ + (int64_t)r * (2 * n - r - 1) / 2 + (c - r - 1)); return {p, p, -1}; }
+          if (r == c) { const int code = -((int)dg_ + r) - 3; return {code, code, slot}; }
+          return {vm::STAGE_ZERO, -1, -1};
+        };
+        auto lsrc = [&](int r, int c) -> Builder::Ent {
+          if (r > c) { const int p = (int)(lo_ + (int64_t)r * (r - 1) / 2 + c); return {p, p, -1}; }
+          if (r == c) return {vm::STAGE_ONE, -1, -1};
+          return {vm::STAGE_ZERO, -1, -1};
+        };
+        const Mat U = B.add_matrix(n, n, usrc, nullptr);
+        const Mat Lm = B.add_matrix(n, n, lsrc, nullptr);
+        B.sjobs.push_back({slot, U.w_off, U.ld + 1, n});
+        const Mat Wp = build_mlp(B, Ld.conditioner, nullptr, nullptr)[0];
+        {
+          B.scratch_reset();
+          const int t = B.scratch(pad8(n));
+          C.fwd.push_back(lin_fwd(U, Ein, t, vm::ACT_IDENTITY, 0, -1));
+          C.fwd.push_back(lin_fwd(Lm, t, Eout, vm::ACT_IDENTITY, 0, -1));
+          C.fwd.push_back(lin_fwd(Wp, Ein + K, Eout, vm::ACT_IDENTITY, 1, -1));
+          C.fwd.push_back(mk(vm::OP_ADD_SCALAR, {slot}));
+          std::vector<NetRows> drows;
+          int c_row;
+          emit_dec_fwd(C.fwd, false, drows, c_row);
+          const int thd = drows.back().post_row;
+          C.fwd.push_back(mk(vm::OP_NORMAL_LP, {Ein + K, nv, thd, thd + nv}));
+        }
+        {
+          B.scratch_reset();
+          const int t = B.scratch(pad8(n)), gt = B.scratch(pad8(n)), gv = B.scratch(pad8(nv)), gw = B.scratch(pad8(nv));
+          C.train.push_back(lin_fwd(U, Ein, t, vm::ACT_IDENTITY, 0, -1));
+          std::vector<NetRows> drows;
+          int c_row;
+          emit_dec_fwd(C.train, true, drows, c_row);
+          const int thd = drows.back().post_row;
+          C.bwd.push_back(mk(vm::OP_NORMAL_LP_BWD, {Ein + K, nv, thd, thd + nv, gv}));
+          emit_mlp_bwd(C.bwd, drows, true);
+          C.bwd.push_back(mk(vm::OP_ADD, {Gout, c_row, K}));                                        // g_z += decoder input gradient
+          C.bwd.push_back(mk(vm::OP_LINEAR_DW, {Ein + K, nv, Gout, Wp.n_out, Wp.w_off, Wp.ld, Wp.b_off}));  // g_W' = y-^T g_z, g_b
+          C.bwd.push_back(lin_bwd_in(Wp, Gout, gw, 0));                                             // g_z W'^T
+          C.bwd.push_back(lin_bwd_in(Lm, Gout, gt, 0));                                             // g_t = g_z L^T
+          C.bwd.push_back(mk(vm::OP_LINEAR_DW, {t, n, Gout, n, Lm.w_off, Lm.ld, -1}));
+          C.bwd.push_back(lin_bwd_in(U, gt, Gin, 0));                                               // g_y+ = g_t U^T
+          C.bwd.push_back(mk(vm::OP_LINEAR_DW, {Ein, n, gt, n, U.w_off, U.ld, -1}));
+          C.bwd.push_back(mk(vm::OP_SCALAR_BWD, {slot}));
+          C.bwd.push_back(mk(vm::OP_COPY, {Gin + K, gv, nv}));                                      // g_y- = decoder score + W' path
+          C.bwd.push_back(mk(vm::OP_ADD, {Gin + K, gw, nv}));
         }
         break;
       }

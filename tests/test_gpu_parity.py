@@ -39,3 +39,10 @@ def test_scaled_wide_configs(name, mode):
   at oracle-sized shapes, through both executors."""
   out = parity.check_config(name, batch=200, check_grad=True, mode=mode, **parity.SMALL[name])
   print(name, mode, out)
+
+
+@pytest.mark.parametrize("mode", ["fused", "layered"])
+def test_mlp_inference_funnel(mode):
+  """MLPInferenceFunnel (mlp.py:40-56) between LULinear layers, as in docs/notebooks/dimension_reduction.ipynb:397-420."""
+  out = parity.check_config("mlpf", batch=300, check_grad=True, mode=mode)
+  print("mlpf", mode, out)

@@ -171,9 +171,18 @@ def test_every_baseline_config_compiles_to_a_plan():
   for name, c in configs.CONFIGS.items():
     spec = fused_chains.spec_of(c["make"](), c["dim"], c["dim_x"])
     plan = _runtime.get_plan(spec)
-    want = {"cfg1": "gen1", "cfg2": "gen1", "cfg3": "gen1", "cfg4": "layered", "cfg5": "layered"}[name]
+    want = {"cfg1": "gen1", "cfg2": "gen1", "cfg3": "gen1", "cfg4": "layered", "cfg5": "layered", "mlpf": "fused"}[name]
     assert plan.executor == want, (name, plan.executor)
     assert plan.launches(False) >= 1 and plan.launches(True) >= 2
+
+
+def test_mlp_inference_funnel_param_tree():
+  m = hk.transform(configs.CONFIGS["mlpf"]["make"](n_lu=1))
+  p = m.init(0, method="log_prob", y=torch.zeros((2, 20)))
+  assert tuple(p["mlp_inference_funnel/~/lu_linear"]["diag_entries"].shape) == (10,)
+  assert tuple(p["mlp_inference_funnel/~/linear"]["w"].shape) == (10, 10)
+  assert tuple(p["mlp_inference_funnel/~/linear"]["b"].shape) == (10,)
+  assert "lu_linear" in p and "lu_linear_1" in p
 
 
 def test_no_cpu_fallback():
