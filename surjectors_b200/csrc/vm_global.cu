@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 
 #include "plan.h"
 #include "vm_ops.cuh"
@@ -233,11 +234,38 @@ inline int chunk_cols(int64_t B, int n_rows) {
   c = std::max<int64_t>(128, std::min(c, cap));
   return (int)c;
 }
+inline bool tc_linear_op(const vm::Op& op) { return op.code == vm::OP_LINEAR && op.a[1] >= 32 && op.a[5] >= 32; }
+
+// tensor-core bookkeeping of one program: tiled-weight offsets (deduplicated by matrix) and scratch sizes
+const VmTcInfo& tc_info(const VmPlan* v, int prog) {
+  VmTcInfo& t = v->tc[prog];
+  if (t.ready) return t;
+  const std::vector<vm::Op>& ops = prog == VM_PROG_BWD ? v->ops_bwd : (prog == VM_PROG_GEN ? v->ops_gen : v->ops_fwd);
+  std::map<int, long long> seen;
+  t.w_off.assign(ops.size(), -1);
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const vm::Op& op = ops[i];
+    if (!tc_linear_op(op)) continue;
+    const int n_in = op.a[1], n_real = op.a[12], tw = op.a[10];
+    const int nkb = (n_in + vmtc::PBK - 1) / vmtc::PBK;
+    auto it = seen.find(tw);
+    if (it == seen.end()) {
+      it = seen.emplace(tw, (long long)t.w_floats).first;
+      t.w_floats += (size_t)((n_real + vmtc::TM - 1) / vmtc::TM) * nkb * vmtc::BLOCK_FLOATS;
+    }
+    t.w_off[i] = it->second;
+    t.max_kpad = std::max(t.max_kpad, nkb * vmtc::PBK);
+  }
+  t.ready = true;
+  return t;
+}
+
 struct Carve {
-  float *par, *grad, *scal, *scal_g, *loss, *rows;
+  float *par, *grad, *scal, *scal_g, *loss, *rows, *w_tiles, *a_tiles;
   size_t total;
 };
-Carve carve(const VmPlan* v, void* ws, int C, bool backward) {
+Carve carve(const VmPlan* v, void* ws, int C, int prog) {
+  const bool backward = prog == VM_PROG_BWD;
   Carve k;
   size_t o = 0;
   auto take = [&](size_t floats) { float* p = ws ? (float*)((char*)ws + o) : nullptr; o += a256(floats * 4); return p; };
@@ -247,13 +275,21 @@ Carve carve(const VmPlan* v, void* ws, int C, bool backward) {
   k.scal_g = take(std::max(v->n_scalars, 1));
   k.loss = take(1);
   k.rows = take((size_t)v->n_rows * C);
+  static const bool pipe_mode = [] { const char* e = getenv("SURJ_B200_TC"); return e && atoi(e) == 5; }();
+  const VmTcInfo& t = tc_info(v, prog);
+  k.w_tiles = take(pipe_mode ? std::max<size_t>(t.w_floats, 1) : 1);
+  k.a_tiles = take(pipe_mode ? std::max<size_t>((size_t)t.max_kpad * 2 * C, 1) : 1);
   k.total = o;
   return k;
 }
 }  // namespace
 
 size_t vm_global_workspace_bytes(const VmPlan* v, int64_t B, bool backward) {
-  return carve(v, nullptr, chunk_cols(B, v->n_rows), backward).total;
+  const int C = chunk_cols(B, v->n_rows);
+  if (backward) return carve(v, nullptr, C, VM_PROG_BWD).total;
+  size_t n = carve(v, nullptr, C, VM_PROG_FWD).total;
+  if (!v->ops_gen.empty()) n = std::max(n, carve(v, nullptr, C, VM_PROG_GEN).total);  // one query covers both directions
+  return n;
 }
 
 int vm_global_launches(const VmPlan* v, int64_t B, bool backward) {
@@ -276,15 +312,16 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
                   const float* eps) {
   const bool backward = prog == VM_PROG_BWD;
   const int C = chunk_cols(B, v->n_rows);
-  Carve k = carve(v, ws, C, backward);
+  Carve k = carve(v, ws, C, prog);
   static const int tc_mode = [] {
-    const char* e = getenv("SURJ_B200_TC");  // 0: FP32 SIMT tiles only; 2: tcgen05 for LINEAR only; 3: for LINEAR_DW only
+    const char* e = getenv("SURJ_B200_TC");  // 0: FP32 SIMT tiles only; 2: tcgen05 for LINEAR only; 3: for LINEAR_DW only; 5: pipelined LINEAR
     return e ? atoi(e) : 1;
   }();
-  const bool use_tc_lin = tc_mode == 1 || tc_mode == 2, use_tc_dw = tc_mode == 1 || tc_mode == 3;
+  const bool use_tc_lin = tc_mode == 1 || tc_mode == 2 || tc_mode == 5, use_tc_dw = tc_mode == 1 || tc_mode == 3 || tc_mode == 5;
   static const bool use_tc = [] {
     const bool on = true;
     if (on) {
+      cudaFuncSetAttribute(vmtc::vg_linear_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::PIPE_SMEM);
       cudaFuncSetAttribute(vmtc::vg_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::SMEM_BYTES);
       cudaFuncSetAttribute(vmtc::vg_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::SMEM_BYTES);
     }
@@ -307,6 +344,23 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
                                                                       k.scal_g, v->n_scalars, k.loss);
   if (!v->sjobs.empty())
     vm::vg_scalars<<<((int)v->sjobs.size() + 31) / 32, 32, 0, st>>>(P.sjobs, (int)v->sjobs.size(), k.par, k.scal);
+  // tensor-core LINEAR ops: split (hi / lo TF32) and tile every weight matrix they use, once per call
+  const VmTcInfo& tci = tc_info(v, prog);
+  // SURJ_B200_TC=5: the TMA-fed pipelined kernel on pre-tiled operands.  Measured (profiles/r1_linear_pipe_ncu.md): it is
+  // L2-bandwidth bound (hi + lo planes of both operands stream per 128x128 tile: 16 FLOP/B) and ends up slower than the
+  // register-staged kernel, which reads each fp32 operand once; it stays opt-in until tiles are shared across a cluster.
+  const bool pipe = use_tc && tc_mode == 5;
+  if (pipe) {
+    std::map<long long, bool> done;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      if (tci.w_off[i] < 0 || done.count(tci.w_off[i])) continue;
+      done[tci.w_off[i]] = true;
+      const vm::Op& op = ops[i];
+      dim3 grid((op.a[12] + vmtc::TM - 1) / vmtc::TM, (op.a[1] + 31) / 32);
+      vmtc::vg_tile<false><<<grid, 256, 0, st>>>(k.par + op.a[10], (size_t)op.a[11], op.a[12], op.a[1],
+                                                 (op.a[1] + vmtc::PBK - 1) / vmtc::PBK, k.w_tiles + tci.w_off[i]);
+    }
+  }
   for (int64_t base = 0; base < B; base += C) {
     const int cols = (int)std::min<int64_t>(C, (B - base + 127) / 128 * 128);  // columns in use (multiple of 128)
     size_t pc = 0;
@@ -314,7 +368,14 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
     while (pc < ops.size()) {
       const vm::Op& op = ops[pc];
       if (op.code == vm::OP_LINEAR) {
-        if (use_tc && use_tc_lin && op.a[1] >= 32 && op.a[5] >= 32) {  // tcgen05 3xTF32 tiles for real contractions
+        if (pipe && tci.w_off[pc] >= 0) {  // tcgen05 3xTF32, TMA-fed pipeline on pre-tiled operands
+          const int nkb = (op.a[1] + vmtc::PBK - 1) / vmtc::PBK;
+          vmtc::vg_tile<true><<<dim3(cols / vmtc::TM, (op.a[1] + 31) / 32), 256, 0, st>>>(k.rows + (size_t)op.a[0] * C, (size_t)C,
+                                                                                       cols, op.a[1], nkb, k.a_tiles);
+          dim3 grid(cols / vmtc::TM, (op.a[5] + vmtc::TN - 1) / vmtc::TN);
+          vmtc::vg_linear_pipe<<<grid, vmtc::PIPE_THREADS, vmtc::PIPE_SMEM, st>>>(op, k.rows, C, k.par, k.a_tiles,
+                                                                                 k.w_tiles + tci.w_off[pc], nkb);
+        } else if (use_tc && use_tc_lin && tc_linear_op(op)) {  // register-staged tcgen05 kernel
           dim3 grid(cols / vmtc::TM, (op.a[5] + vmtc::TN - 1) / vmtc::TN);
           vmtc::vg_linear_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, k.par);
         } else {

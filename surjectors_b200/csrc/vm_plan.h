@@ -6,6 +6,14 @@
 
 #include "vm.cuh"
 
+// Which OP_LINEAR ops of a program run on the pipelined tcgen05 kernel and where their tiled weight copy lives
+struct VmTcInfo {
+  bool ready = false;
+  std::vector<long long> w_off;  // per op: float offset of its tiled [out][in] weights inside the weight-tile region, -1 = not a tensor-core op
+  size_t w_floats = 0;           // size of the weight-tile region
+  int max_kpad = 0;              // max over tensor-core ops of n_in rounded up to 32 (activation tiles need kpad * 2 floats per sample)
+};
+
 struct VmPlan {
   std::vector<vm::Op> ops_fwd, ops_bwd, ops_gen;  // log_prob, its VJP, sampling direction (empty: unsupported)
   std::string gen_why;
@@ -27,6 +35,7 @@ struct VmPlan {
   const vm::Op* d_ops_bwd = nullptr;
   const vm::Op* d_ops_gen = nullptr;
   int n_sm = 148, occ_fwd = 1, occ_bwd = 1, occ_gen = 1;
+  mutable VmTcInfo tc[3];  // per program (VM_PROG_*), filled on first use by the per-op executor
 };
 
 // vm_global.cu

@@ -363,4 +363,199 @@ vg_dw_tc(vm::Op op, const float* __restrict__ rows, int C, int cols, int slab, f
   tmem_free(tmem_d, warp);
 }
 
+// =====================================================================================
+// Pipelined LINEAR: operands are split (hi / lo TF32) and tiled ONCE into the canonical UMMA layout in
+// global memory, so the GEMM's K loop is pure data movement + MMA:
+//   producer thread   cp.async.bulk (TMA unit, no tensor map needed: a tile is 16 KB contiguous) into a
+//                     3-stage shared-memory ring, completion on the stage's `full` mbarrier
+//   MMA thread        waits `full`, issues the 12 tcgen05.mma of the K block into TMEM buffer kb & 1,
+//                     tcgen05.commit -> the stage's `empty` mbarrier and the buffer's `tmem_full` mbarrier
+//   4 drain warps     tcgen05.ld the finished buffer, add it into FP32 registers (round-to-nearest; see the
+//                     note on the truncating tensor-core accumulator above), arrive on `tmem_empty`
+// Tiled operand layout: block (row_tile, k_block) = [hi 4096 floats | lo 4096 floats], element (r, k) of a
+// plane at tile_off(r, k); blocks ordered [row_tile][k_block].
+constexpr int PIPE_STAGES = 3;
+constexpr int PBK = 16;                              // K block of the pipelined kernel: 32 KB per stage -> 2 CTAs per SM,
+                                                     // so one CTA's prologue / epilogue hides behind the other's MMAs
+constexpr int TILE_FLOATS = TM * PBK;                // one plane of one block
+constexpr int BLOCK_FLOATS = 2 * TILE_FLOATS;        // hi + lo
+constexpr size_t PIPE_SMEM = (size_t)PIPE_STAGES * 2 * BLOCK_FLOATS * 4 + 1024 + 256;
+constexpr int PIPE_THREADS = 192;                    // warp 0 producer, warp 1 MMA, warps 2..5 drain (lanes 32 * (w % 4))
+
+__device__ __forceinline__ int ptile_off(int r, int k) {  // canonical K-major layout of a 128 x PBK plane
+  return (r >> 3) * (PBK * 8) + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
+}
+__device__ __forceinline__ uint64_t pmake_desc(uint32_t saddr) {  // LBO 128 B, SBO = PBK / 4 core matrices = PBK * 32 B
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | ((uint64_t)(PBK * 2) << 32) | (1ull << 46);
+}
+
+// rows x K source -> tiled planes.  TRANSPOSED: src[k * pitch + r] (rows contiguous), else src[r * pitch + k].
+// grid (row tiles, ceil(K / 32)): a CTA converts 128 rows x 32 k = two K blocks.
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256)
+vg_tile(const float* __restrict__ src, size_t pitch, int n_rows, int K, int nkb, float* __restrict__ dst) {
+  const int rt = blockIdx.x;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + it * 256;
+    int r, c4;
+    if (TRANSPOSED) { r = idx & (TM - 1); c4 = idx >> 7; }
+    else { r = (idx & 7) + 8 * (idx >> 6); c4 = (idx >> 3) & 7; }
+    const int row = rt * TM + r, k0 = blockIdx.y * 32 + 4 * c4;
+    const int kb = k0 / PBK;
+    if (kb >= nkb) continue;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n_rows) {
+      if (TRANSPOSED) {
+        const float* p = src + (size_t)k0 * pitch + row;
+        if (k0 + 0 < K) v.x = p[0];
+        if (k0 + 1 < K) v.y = p[pitch];
+        if (k0 + 2 < K) v.z = p[2 * pitch];
+        if (k0 + 3 < K) v.w = p[3 * pitch];
+      } else {
+        const float* p = src + (size_t)row * pitch + k0;
+        if (k0 + 3 < K) v = *reinterpret_cast<const float4*>(p);
+        else {
+          if (k0 + 0 < K) v.x = p[0];
+          if (k0 + 1 < K) v.y = p[1];
+          if (k0 + 2 < K) v.z = p[2];
+        }
+      }
+    }
+    float4 h, l;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+    float* blk = dst + ((size_t)rt * nkb + kb) * BLOCK_FLOATS;
+    const int o = ptile_off(r, k0 - kb * PBK);
+    *reinterpret_cast<float4*>(blk + o) = h;
+    *reinterpret_cast<float4*>(blk + TILE_FLOATS + o) = l;
+  }
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// out[j][s] = act(b[j] (+ prev) + sum_i W[i][j] in[i][s]) from tiled operands.
+// a_tiles: activations, row tiles = 128-sample tiles;  b_tiles: the [out][in] weight copy, row tiles = 128 outputs.
+// grid (sample tiles, output tiles); op fields as OP_LINEAR (a5 = padded outputs, a12 = real outputs).
+__global__ void __launch_bounds__(PIPE_THREADS, 2)
+vg_linear_pipe(vm::Op op, float* __restrict__ rows, int C, const float* __restrict__ par, const float* __restrict__ a_tiles,
+               const float* __restrict__ b_tiles, int nkb) {
+  extern __shared__ unsigned char smem_raw[];
+  uintptr_t base = ((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023;
+  float* stage_mem = (float*)base;  // [PIPE_STAGES][A block | B block]
+  uint64_t* bars = (uint64_t*)(stage_mem + (size_t)PIPE_STAGES * 2 * BLOCK_FLOATS);
+  uint64_t* full = bars;                       // [PIPE_STAGES]
+  uint64_t* empty = bars + PIPE_STAGES;        // [PIPE_STAGES]
+  uint64_t* tmem_full = bars + 2 * PIPE_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  const int out_row = op.a[4], n_out = op.a[5], b_off = op.a[6], act = op.a[7], accumulate = op.a[8], pre_row = op.a[9];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
+  const int n_valid = min(TN, n_out - j0);
+  const int n_tile = (n_valid + 15) & ~15;
+  if (tid == 0) {
+    for (int s = 0; s < PIPE_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 4); }
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- producer
+      const float* a_src = a_tiles + (size_t)blockIdx.x * nkb * BLOCK_FLOATS;
+      const float* b_src = b_tiles + (size_t)blockIdx.y * nkb * BLOCK_FLOATS;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % PIPE_STAGES;
+        if (kb >= PIPE_STAGES) mbar_wait(empty + s, ((kb / PIPE_STAGES) - 1) & 1);
+        float* sa = stage_mem + (size_t)s * 2 * BLOCK_FLOATS;
+        mbar_expect_tx(full + s, 2 * BLOCK_FLOATS * 4);
+        bulk_g2s(sa, a_src + (size_t)kb * BLOCK_FLOATS, BLOCK_FLOATS * 4, full + s);
+        bulk_g2s(sa + BLOCK_FLOATS, b_src + (size_t)kb * BLOCK_FLOATS, BLOCK_FLOATS * 4, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer
+      const uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % PIPE_STAGES, buf = kb & 1;
+        mbar_wait(full + s, (kb / PIPE_STAGES) & 1);
+        if (kb >= 2) mbar_wait(tmem_empty + buf, ((kb >> 1) - 1) & 1);
+        tc_fence_after();
+        const float* sa = stage_mem + (size_t)s * 2 * BLOCK_FLOATS;
+        const uint64_t da_hi = pmake_desc(smem_u32(sa)), da_lo = pmake_desc(smem_u32(sa + TILE_FLOATS));
+        const uint64_t db_hi = pmake_desc(smem_u32(sa + BLOCK_FLOATS)), db_lo = pmake_desc(smem_u32(sa + BLOCK_FLOATS + TILE_FLOATS));
+        const uint32_t d = tmem_base + (uint32_t)(buf * TN);
+#pragma unroll
+        for (int ks = 0; ks < PBK / 8; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * 16);
+          mma_tf32(d, da_lo + adv, db_hi + adv, idesc, ks > 0 ? 1u : 0u);
+          mma_tf32(d, da_hi + adv, db_lo + adv, idesc, 1u);
+          mma_tf32(d, da_hi + adv, db_hi + adv, idesc, 1u);
+        }
+        umma_commit(empty + s);          // shared-memory stage free once these MMAs have read it
+        umma_commit(tmem_full + buf);    // accumulator of this K block complete
+      }
+    }
+  } else {  // ---- drain warps 2..5
+    const int lane_base = 32 * (warp & 3);
+    float acc[TN];
+#pragma unroll
+    for (int c = 0; c < TN; ++c) acc[c] = 0.0f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int buf = kb & 1;
+      mbar_wait(tmem_full + buf, (kb >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        if (c0 < n_tile) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * TN + c0), v);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) acc[c0 + q] += v[q];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + buf);
+    }
+    const size_t col = (size_t)s0 + lane_base + lane;
+    const int acc_row = pre_row >= 0 ? pre_row : out_row;
+#pragma unroll
+    for (int c = 0; c < TN; ++c) {
+      const int j = j0 + c;
+      if (c < n_valid) {
+        float x = acc[c] + (b_off >= 0 ? __ldg(par + b_off + j) : 0.0f);
+        if (accumulate) x += rows[(size_t)(acc_row + j) * C + col];
+        if (pre_row >= 0) rows[(size_t)(pre_row + j) * C + col] = x;
+        rows[(size_t)(out_row + j) * C + col] = vm::act_fwd(act, x);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
 }  // namespace vmtc
