@@ -142,7 +142,7 @@ def lib():
         f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "(there is no CPU fallback)"
       )
-    _lib = _bind(C.CDLL(LIB_PATH), _SIGNATURES)
+    _lib = _bind(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL), _SIGNATURES)
   return _lib
 
 

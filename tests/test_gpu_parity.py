@@ -46,3 +46,17 @@ def test_mlp_inference_funnel(mode):
   """MLPInferenceFunnel (mlp.py:40-56) between LULinear layers, as in docs/notebooks/dimension_reduction.ipynb:397-420."""
   out = parity.check_config("mlpf", batch=300, check_grad=True, mode=mode)
   print("mlpf", mode, out)
+
+
+def test_user_built_generated_kernel_parity(tmp_path):
+  """fused_chains.build_fused_kernel: a non-BASELINE chain gets its own generated straight-line kernel (nvcc at the
+  user's request), which must agree with the oracle like the built-in ones."""
+  import torch
+
+  from surjectors_b200 import configs, fused_chains, hk
+
+  scale = dict(dim=12, cond_hidden=(6, 6), dec_hidden=(4, 4))
+  m = hk.transform(configs.make_cfg2(**scale))
+  fused_chains.build_fused_kernel(m, dict(y=torch.zeros((2, 12))), cache_dir=str(tmp_path))
+  out = parity.check_config("cfg2", batch=500, check_grad=True, mode="gen1", **scale)
+  print("user-built", out)

@@ -202,3 +202,17 @@ def test_bad_descriptor_is_rejected_by_the_c_abi():
   spec.layers[1].dim_in = 11  # the chain delivers 10
   with pytest.raises(ValueError, match="delivers"):
     _runtime.Plan(spec)
+
+
+def test_build_fused_kernel_for_a_user_chain(tmp_path):
+  """A chain that is not a BASELINE config gets its own generated kernel at the user's request (nvcc, no GPU needed)."""
+  def flow(method, **kw):
+    t = sj.Chain([sj.Slice(3, configs._decoder_fn(4, (6, 6))), sj.LULinear(3)])
+    return sj.TransformedDistribution(_base(3), t)(method=method, **kw)
+
+  m = hk.transform(flow)
+  batch = dict(y=torch.zeros((2, 7)))
+  traced, _ = m.trace(method="log_prob", **batch)
+  assert _runtime.Plan(traced[0]).executor == "fused"
+  fused_chains.build_fused_kernel(m, batch, cache_dir=str(tmp_path))
+  assert _runtime.Plan(traced[0]).executor == "gen1"
