@@ -154,6 +154,40 @@ def make_mlpf(dim=20, n_keep=10, dec_hidden=(8, 8), n_lu=2):
   return flow
 
 
+def make_cond(dim=12, dx=3, hidden=(8, 8), n_bins=4):
+  def _unstack_fn(params):
+    means, log_scales = S.unstack(params, -1)
+    return S.ScalarAffine(means, torch.exp(log_scales))
+
+  def _split_inv(params):
+    a, b = S.split(params, 2, -1)
+    return S.Inverse(S.ScalarAffine(a, torch.exp(b)))
+
+  def flow(y, x=None):
+    d = dim
+    layers = [S.AffineMaskedAutoregressiveInferenceFunnel(d - 2, _dec(2, hidden), S.MADE(d - 2, list(hidden), 2))]
+    d -= 2
+    layers += [
+      S.MaskedCoupling(S.make_alternating_binary_mask(d, True), S.make_mlp(list(hidden) + [2 * d]), _split_inv),
+      S.RationalQuadraticSplineMaskedCoupling(
+        S.make_alternating_binary_mask(d),
+        hk.Sequential([S.make_mlp(list(hidden) + [d * (3 * n_bins + 1)]), hk.Reshape((d, 3 * n_bins + 1))]), -3.0, 3.0),
+      S.AffineMaskedCouplingInferenceFunnel(d - 3, _dec(3, hidden), S.make_mlp(list(hidden) + [2 * d])),
+    ]
+    d -= 3
+    layers += [
+      S.MaskedAutoregressive(S.MADE(d, list(hidden), 2), _unstack_fn),
+      S.LULinear(d),
+      S.Permutation(np.arange(d)[::-1], 1),
+      S.Slice(d - 2, _dec(2, hidden)),
+    ]
+    d -= 2
+    td = S.TransformedDistribution(S.standard_normal_base(d, y.dtype), S.Chain(layers))
+    return td.log_prob(y, x)
+
+  return flow
+
+
 def randomize(params, seed, w_std=0.3, b_val=None, b_std=0.1):
   """Replace haiku-default inits by non-trivial values so every transform is exercised
   (mirrors masked_coupling_test.py:78-82: TruncatedNormal(1.0) weights, ones bias)."""

@@ -172,6 +172,42 @@ def make_mlpf(dim=20, n_keep=10, dec_hidden=(8, 8), n_lu=2):
   return flow
 
 
+def make_cond(dim=12, dx=3, hidden=(8, 8), n_bins=4):
+  """Every layer kind on the path with a conditioning input x (the reference's conditional density estimation
+  pattern, examples/conditional_density_estimation.py:28-76): AR funnel, coupling, spline coupling, coupling funnel,
+  MAF, LULinear, Permutation, Slice."""
+
+  def _unstack_fn(params):
+    means, log_scales = unstack(params, -1)
+    return distrax.ScalarAffine(means, jnp.exp(log_scales))
+
+  def flow(method, **kwargs):
+    d = dim
+    layers = [
+      AffineMaskedAutoregressiveInferenceFunnel(d - 2, _decoder_fn(2, hidden), MADE(d - 2, list(hidden), 2)),
+    ]
+    d -= 2
+    layers += [
+      MaskedCoupling(make_alternating_binary_mask(d, True), make_mlp(list(hidden) + [2 * d]),
+                     lambda p: distrax.Inverse(distrax.ScalarAffine(*(lambda a, b: (a, jnp.exp(b)))(*jnp.split(p, 2, -1))))),
+      RationalQuadraticSplineMaskedCoupling(
+        make_alternating_binary_mask(d), hk.Sequential([make_mlp(list(hidden) + [d * (3 * n_bins + 1)]),
+                                                        hk.Reshape((d, 3 * n_bins + 1))]), -3.0, 3.0),
+      AffineMaskedCouplingInferenceFunnel(d - 3, _decoder_fn(3, hidden), make_mlp(list(hidden) + [2 * d])),
+    ]
+    d -= 3
+    layers += [
+      MaskedAutoregressive(MADE(d, list(hidden), 2), _unstack_fn),
+      LULinear(d),
+      Permutation(np.arange(d)[::-1], 1),
+      Slice(d - 2, _decoder_fn(2, hidden)),
+    ]
+    d -= 2
+    return TransformedDistribution(_base(d), Chain(layers))(method=method, **kwargs)
+
+  return flow
+
+
 CONFIGS = {
   "cfg1": dict(make=make_cfg1, dim=10, dim_x=0, batch=4096),
   "cfg2": dict(make=make_cfg2, dim=20, dim_x=0, batch=65536),
@@ -179,4 +215,5 @@ CONFIGS = {
   "cfg4": dict(make=make_cfg4, dim=64, dim_x=0, batch=1 << 20),
   "cfg5": dict(make=make_cfg5, dim=128, dim_x=16, batch=1 << 23),
   "mlpf": dict(make=make_mlpf, dim=20, dim_x=0, batch=65536),
+  "cond": dict(make=make_cond, dim=12, dim_x=3, batch=65536),
 }

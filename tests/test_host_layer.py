@@ -171,7 +171,7 @@ def test_every_baseline_config_compiles_to_a_plan():
   for name, c in configs.CONFIGS.items():
     spec = fused_chains.spec_of(c["make"](), c["dim"], c["dim_x"])
     plan = _runtime.get_plan(spec)
-    want = {"cfg1": "gen1", "cfg2": "gen1", "cfg3": "gen1", "cfg4": "layered", "cfg5": "layered", "mlpf": "fused"}[name]
+    want = {"cfg1": "gen1", "cfg2": "gen1", "cfg3": "gen1", "cfg4": "layered", "cfg5": "layered", "mlpf": "fused", "cond": "fused"}[name]
     assert plan.executor == want, (name, plan.executor)
     assert plan.launches(False) >= 1 and plan.launches(True) >= 2
 
