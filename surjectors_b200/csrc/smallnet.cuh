@@ -38,8 +38,11 @@ enum : int { LAYOUT_SPLIT = 0, LAYOUT_INTERLEAVED = 1 };
 #define SURJ_HALF_LOG_2PI 0.91893853320467274178f
 
 // ------------------------------------------------------------------ scalar math
+// exp feeds log-dets and Gaussian residuals directly: full-accuracy expf.  The sigmoid of swish / sigmoid activations
+// only shapes hidden units: ex2.approx + approximate reciprocal (a few ulp) -- measured to leave the log-prob error
+// at the 1e-7 level while removing a third of the straight-line instruction stream.
 SURJ_DEV float fast_exp(float x) { return expf(x); }
-SURJ_DEV float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+SURJ_DEV float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 SURJ_DEV float softplus_f(float x) { return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x))); }
 
 template <int ACT>
