@@ -119,7 +119,8 @@ enum SurjPlanMode {
   SURJ_MODE_AUTO = 0,  /* fused whole-chain kernel when one is compiled in for this chain, else per-layer */
   SURJ_MODE_FUSED = 1, /* require the fused whole-chain kernel (error if not compiled in) */
   SURJ_MODE_LAYERED = 2, /* generic per-layer kernels (any width) */
-  SURJ_MODE_FUSED_GEN1 = 3 /* the build-time generated straight-line kernel for this chain (A/B comparison) */
+  SURJ_MODE_FUSED_GEN1 = 3, /* the build-time generated straight-line kernel for this chain (A/B comparison) */
+  SURJ_MODE_FUSED_COMPACT = 4 /* the compact looped kernel for affine coupling / coupling-funnel chains (error if outside its family) */
 };
 
 /* What is added to the summed likelihood contributions of the layers. */
@@ -136,7 +137,7 @@ void surj_plan_destroy(SurjPlan* plan);
 uint64_t surj_plan_key(const SurjPlan* plan);
 int surj_chain_key(const SurjLayerDesc* layers, int32_t n_layers, int32_t dim_in, int32_t dim_x, int64_t n_params,
                    uint64_t* key_out);
-/* 0 = per-layer kernels, 1 = generated straight-line fused kernel, 2 = fused interpreter kernel */
+/* 0 = per-layer kernels, 1 = generated straight-line fused kernel, 2 = fused interpreter kernel, 3 = compact looped fused kernel */
 int32_t surj_plan_is_fused(const SurjPlan* plan);
 int32_t surj_plan_dim_out(const SurjPlan* plan);
 /* number of kernels one fwd / one bwd call launches (for launch accounting) */

@@ -188,6 +188,41 @@ def make_cond(dim=12, dx=3, hidden=(8, 8), n_bins=4):
   return flow
 
 
+def make_cpl(dim=12, hidden=(16, 16), dec_hidden=(8, 8), activation="tanh"):
+  act = {"tanh": torch.tanh, "relu": hk.relu, "swish": hk.swish}[activation]
+
+  def _split_inv(params):
+    a, b = S.split(params, 2, -1)
+    return S.Inverse(S.ScalarAffine(a, torch.exp(b)))
+
+  def _unstack_fn(params):
+    means, log_scales = S.unstack(params, -1)
+    return S.ScalarAffine(means, torch.exp(log_scales))
+
+  def _mlp(dims):
+    return S.make_mlp(dims, activation=act)
+
+  def flow(y, x=None):
+    d = dim
+    layers = [
+      S.MaskedCoupling(S.make_alternating_binary_mask(d, True), _mlp(list(hidden) + [2 * d]), _split_inv),
+      S.AffineMaskedCouplingInferenceFunnel(
+        d - 4, S.normal_decoder(4, conditioner_factory=lambda: _mlp(list(dec_hidden) + [8])), _mlp(list(hidden) + [2 * d])),
+    ]
+    d -= 4
+    layers += [
+      S.MaskedCoupling(S.make_alternating_binary_mask(d), hk.Sequential([_mlp(list(hidden) + [2 * d]), hk.Reshape((d, 2))]),
+                       _unstack_fn),
+      S.AffineMaskedCouplingInferenceFunnel(
+        d - 3, S.normal_decoder(3, conditioner_factory=lambda: _mlp(list(dec_hidden) + [6])), _mlp(list(hidden) + [2 * d])),
+    ]
+    d -= 3
+    td = S.TransformedDistribution(S.standard_normal_base(d, y.dtype), S.Chain(layers))
+    return td.log_prob(y, x)
+
+  return flow
+
+
 def randomize(params, seed, w_std=0.3, b_val=None, b_std=0.1):
   """Replace haiku-default inits by non-trivial values so every transform is exercised
   (mirrors masked_coupling_test.py:78-82: TruncatedNormal(1.0) weights, ones bias)."""

@@ -25,7 +25,7 @@ ACT = {
   "identity": 0, "relu": 1, "swish": 2, "tanh": 3, "sigmoid": 4, "softplus": 5, "gelu": 6, "elu": 7,
   "leaky_relu": 8,
 }
-MODE_AUTO, MODE_FUSED, MODE_LAYERED, MODE_FUSED_GEN1 = range(4)
+MODE_AUTO, MODE_FUSED, MODE_LAYERED, MODE_FUSED_GEN1, MODE_FUSED_COMPACT = range(5)
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = 0, -1, -2, -3, -4
 
 

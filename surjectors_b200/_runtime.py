@@ -9,6 +9,7 @@ no CPU or eager path -- a call on CPU tensors, or with the library missing, rais
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 
 import torch
@@ -22,7 +23,10 @@ _plans = {}
 _plans_lock = threading.Lock()
 _default_mode = _abi.MODE_AUTO
 
-MODES = {"auto": _abi.MODE_AUTO, "fused": _abi.MODE_FUSED, "layered": _abi.MODE_LAYERED, "gen1": _abi.MODE_FUSED_GEN1}
+MODES = {"auto": _abi.MODE_AUTO, "fused": _abi.MODE_FUSED, "layered": _abi.MODE_LAYERED, "gen1": _abi.MODE_FUSED_GEN1,
+         "compact": _abi.MODE_FUSED_COMPACT}
+if os.environ.get("SURJ_B200_MODE"):  # A/B measurements of the executors without touching the caller's code
+  _default_mode = MODES[os.environ["SURJ_B200_MODE"]]
 
 
 class execution_mode:
@@ -59,7 +63,7 @@ class Plan:
     self.spec = spec
     self.base = base
     self.dim_in, self.dim_x, self.dim_out, self.n_params = spec.dim_in, spec.dim_x, spec.dim_out, spec.n_params
-    self.executor = {0: "layered", 1: "gen1", 2: "fused"}[int(lib.surj_plan_is_fused(handle))]
+    self.executor = {0: "layered", 1: "gen1", 2: "fused", 3: "compact"}[int(lib.surj_plan_is_fused(handle))]
     self.is_fused = self.executor != "layered"
     self.key = int(lib.surj_plan_key(handle))
     self._ws = {}

@@ -28,6 +28,7 @@ from surjectors_b200 import (
   TransformedDistribution,
   hk,
 )
+from surjectors_b200 import _sym
 from surjectors_b200.compat import distrax, jnp, tfd
 from surjectors_b200.nn import MADE, make_mlp
 from surjectors_b200.util import make_alternating_binary_mask, unstack
@@ -208,7 +209,49 @@ def make_cond(dim=12, dx=3, hidden=(8, 8), n_bins=4):
   return flow
 
 
+def make_cpl(dim=12, hidden=(16, 16), dec_hidden=(8, 8), activation="tanh"):
+  """A user-style affine coupling / funnel chain off the BASELINE shapes: another activation and hidden widths, an
+  Inverse(ScalarAffine) inner bijector and an unstack-ed (interleaved) conditioner output -- the family of the compact
+  fused kernel (csrc/compact.cuh)."""
+  act = {"tanh": _sym.tanh, "relu": _sym.relu, "swish": _sym.swish}[activation]
+
+  def _split_inv(params):
+    a, b = jnp.split(params, 2, -1)
+    return distrax.Inverse(distrax.ScalarAffine(a, jnp.exp(b)))
+
+  def _unstack_fn(params):
+    means, log_scales = unstack(params, -1)
+    return distrax.ScalarAffine(means, jnp.exp(log_scales))
+
+  def _dec(n_dim):
+    net = make_mlp(list(dec_hidden) + [n_dim * 2], activation=act)
+
+    def _fn(z):
+      mu, log_scale = jnp.split(net(z), 2, -1)
+      return tfd.Independent(tfd.Normal(mu, jnp.exp(log_scale)))
+
+    return _fn
+
+  def flow(method, **kwargs):
+    d = dim
+    layers = [
+      MaskedCoupling(make_alternating_binary_mask(d, True), make_mlp(list(hidden) + [2 * d], activation=act), _split_inv),
+      AffineMaskedCouplingInferenceFunnel(d - 4, _dec(4), make_mlp(list(hidden) + [2 * d], activation=act)),
+    ]
+    d -= 4
+    layers += [
+      MaskedCoupling(make_alternating_binary_mask(d), hk.Sequential([make_mlp(list(hidden) + [2 * d], activation=act),
+                                                                      hk.Reshape((d, 2))]), _unstack_fn),
+      AffineMaskedCouplingInferenceFunnel(d - 3, _dec(3), make_mlp(list(hidden) + [2 * d], activation=act)),
+    ]
+    d -= 3
+    return TransformedDistribution(_base(d), Chain(layers))(method=method, **kwargs)
+
+  return flow
+
+
 CONFIGS = {
+  "cpl": dict(make=make_cpl, dim=12, dim_x=0, batch=4096),
   "cfg1": dict(make=make_cfg1, dim=10, dim_x=0, batch=4096),
   "cfg2": dict(make=make_cfg2, dim=20, dim_x=0, batch=65536),
   "cfg3": dict(make=make_cfg3, dim=20, dim_x=0, batch=65536),

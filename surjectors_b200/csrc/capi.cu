@@ -9,6 +9,7 @@
 #include <vector>
 #include <string>
 
+#include "compact.h"
 #include "plan.h"
 #include "vm_plan.h"
 
@@ -307,18 +308,23 @@ extern "C" int surj_plan_create(const SurjLayerDesc* layers, int32_t n_layers, i
   p->mode = mode;
   p->base = base;
   surj_chain_key(p->layers.data(), n_layers, dim_in, dim_x, n_params, &p->key);
-  // Every chain compiles to one program (vm_plan.cu) with two executors.  AUTO picks, in order: a
-  // generated straight-line kernel compiled in for exactly this chain, the fused interpreter kernel
-  // (parameters + a tile of activations fit in shared memory), the per-op executor (any width).
+  // Every chain compiles to one program (vm_plan.cu) with two executors; two more kernels cover special families.
+  // AUTO picks, in order: a generated straight-line kernel compiled in for exactly this chain, the compact looped kernel
+  // (affine coupling / coupling-funnel chains with small two-hidden-layer MLPs, no code generation needed), the fused
+  // interpreter kernel (parameters + a tile of activations fit in shared memory), the per-op executor (any width).
   std::string why;
   p->vmp = vm_compile(p, &why);
   if (mode == SURJ_MODE_AUTO || mode == SURJ_MODE_FUSED_GEN1) p->fused = surj_find_small(p->key);
+  std::string cc_why;
+  if (mode == SURJ_MODE_AUTO || mode == SURJ_MODE_FUSED_COMPACT) p->ccp = cc_compile(p, &cc_why);
   if (p->fused) p->exec = 1;
+  else if (p->ccp) p->exec = 4;
   else if (p->vmp && p->vmp->fused_ok && (mode == SURJ_MODE_AUTO || mode == SURJ_MODE_FUSED)) p->exec = 2;
   else if (p->vmp && (mode == SURJ_MODE_AUTO || mode == SURJ_MODE_LAYERED)) p->exec = 3;
   if (p->exec == 0) {
     char buf[400];
     if (!p->vmp) snprintf(buf, sizeof buf, "chain is not supported: %s", why.c_str());
+    else if (mode == SURJ_MODE_FUSED_COMPACT) snprintf(buf, sizeof buf, "chain cannot run on the compact fused kernel: %s", cc_why.c_str());
     else if (mode == SURJ_MODE_FUSED_GEN1)
       snprintf(buf, sizeof buf, "no generated kernel compiled in for chain key 0x%016llx (%d registered)",
                (unsigned long long)p->key, surj_registry_count());
@@ -334,13 +340,14 @@ extern "C" int surj_plan_create(const SurjLayerDesc* layers, int32_t n_layers, i
 
 extern "C" void surj_plan_destroy(SurjPlan* plan) {
   if (!plan) return;
+  cc_destroy(plan->ccp);
   vm_destroy(plan->vmp);
   delete plan;
 }
 extern "C" uint64_t surj_plan_key(const SurjPlan* plan) { return plan ? plan->key : 0; }
 extern "C" int32_t surj_plan_is_fused(const SurjPlan* plan) {
   if (!plan) return 0;
-  return plan->exec == 3 ? 0 : plan->exec;
+  return plan->exec == 3 ? 0 : (plan->exec == 4 ? 3 : plan->exec);
 }
 extern "C" int32_t surj_plan_dim_out(const SurjPlan* plan) { return plan ? plan->dim_out : -1; }
 
@@ -351,8 +358,12 @@ static int ensure_device(const SurjPlan* p) {
   if (e != cudaSuccess) return surj_cuda_fail(e, "cudaGetDevice");
   e = cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return surj_cuda_fail(e, "cudaDeviceGetAttribute");
-  if (p->exec >= 2) {
+  if (p->exec == 2 || p->exec == 3) {
     int r = vm_prepare(p->vmp);
+    if (r) return r;
+  }
+  if (p->exec == 4) {
+    int r = cc_prepare(p->ccp);
     if (r) return r;
   }
   if (p->exec == 1) {
@@ -371,6 +382,7 @@ static int ensure_device(const SurjPlan* p) {
 
 static int fused_grid(const SurjPlan* p, int64_t B, bool backward) {
   if (p->exec == 2) return vm_grid(p->vmp, B, backward ? VM_PROG_BWD : VM_PROG_FWD);
+  if (p->exec == 4) return cc_grid(p->ccp, B, backward);
   const int nt = p->fused->nt;
   const int64_t tiles = (B + nt - 1) / nt;
   const int64_t cap = (int64_t)p->n_sm * (backward ? p->bwd_blocks : p->fwd_blocks);
@@ -381,11 +393,12 @@ static size_t fused_bwd_workspace(int64_t rows, int npad, int np);
 
 extern "C" size_t surj_plan_workspace_bytes(const SurjPlan* plan, int64_t batch, int32_t backward) {
   if (!plan || batch <= 0) return 0;
-  if (plan->exec == 1 || plan->exec == 2) {
+  if (plan->exec == 1 || plan->exec == 2 || plan->exec == 4) {
     if (!backward) return 0;
     int64_t rows;
     if (ensure_device(plan) == SURJ_OK) rows = fused_grid(plan, batch, true);
     else if (plan->exec == 2) rows = vm_max_grid(plan->vmp, batch);
+    else if (plan->exec == 4) rows = cc_max_grid(plan->ccp);
     else {  // no device yet: an upper bound of one partial row per possible CTA
       const int64_t tiles = (batch + plan->fused->nt - 1) / plan->fused->nt;
       rows = tiles < 4096 ? tiles : 4096;
@@ -397,7 +410,7 @@ extern "C" size_t surj_plan_workspace_bytes(const SurjPlan* plan, int64_t batch,
 
 extern "C" int32_t surj_plan_launches(const SurjPlan* plan, int32_t backward) {
   if (!plan) return 0;
-  if (plan->exec == 1 || plan->exec == 2) return backward ? 2 : 1;
+  if (plan->exec == 1 || plan->exec == 2 || plan->exec == 4) return backward ? 2 : 1;
   return vm_global_launches(plan->vmp, 1, backward != 0);
 }
 
@@ -423,6 +436,12 @@ extern "C" int surj_chain_logprob_fwd(const SurjPlan* plan, SurjStream stream, c
     return SURJ_E_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (plan->exec == 4) {
+    r = ensure_device(plan);
+    if (r) return r;
+    return cc_launch(plan->ccp, st, 0, plan->base == SURJ_BASE_STANDARD_NORMAL, y, params, nullptr, 0.0f, nullptr, z_out, lp_out,
+                     nullptr, nullptr, 0, batch, nullptr, 0);
+  }
   if (plan->exec == 2) {
     r = ensure_device(plan);
     if (r) return r;
@@ -591,6 +610,10 @@ static int fused_backward(const SurjPlan* plan, cudaStream_t st, const float* y,
     r = vm_launch(plan->vmp, st, VM_PROG_BWD, with_base, y, x, params, g_lp, g_scale, g_z, nullptr, lp_out, g_y, g_x, partials,
                   npad, batch, grid, tickets, ncb + 1);
     if (r) return r;
+  } else if (plan->exec == 4) {
+    r = cc_launch(plan->ccp, st, 1, with_base, y, params, g_lp, g_scale, g_z, nullptr, lp_out, g_y, partials, npad, batch, tickets,
+                  ncb + 1);
+    if (r) return r;
   } else {
     cudaError_t e = plan->fused->bwd(grid, st, with_base, y, x, params, g_lp, g_scale, g_z, partials, npad, lp_out,
                                      nullptr, g_y, g_x, batch, tickets, ncb + 1);
@@ -614,7 +637,7 @@ extern "C" int surj_chain_logprob_bwd(const SurjPlan* plan, SurjStream stream, c
     return SURJ_E_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan->exec == 1 || plan->exec == 2)
+  if (plan->exec == 1 || plan->exec == 2 || plan->exec == 4)
     return fused_backward(plan, st, y, x, params, g_lp, g_scale, g_z, g_params, loss_out, lp_out, g_y, g_x, workspace,
                           workspace_bytes, batch, AdamArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0}, DpArgs{});
   r = ensure_device(plan);
@@ -676,7 +699,7 @@ extern "C" int surj_train_step(const SurjPlan* plan, SurjStream stream, const fl
     return SURJ_E_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan->exec == 1 || plan->exec == 2)
+  if (plan->exec == 1 || plan->exec == 2 || plan->exec == 4)
     return fused_backward(plan, st, y, x, params, nullptr, g_scale, nullptr, g_params, loss_out, nullptr, nullptr,
                           nullptr, workspace, workspace_bytes, batch, AdamArgs{params, mu, nu, count, lr, b1, b2, eps}, DpArgs{});
   r = surj_chain_logprob_bwd(plan, stream, y, x, params, nullptr, g_scale, nullptr, g_params, loss_out, nullptr, nullptr,
@@ -816,7 +839,7 @@ extern "C" int surj_train_step_dp(const SurjPlan* plan, SurjDp* d, SurjStream st
     surj_set_error("surj_train_step_dp: connect the SurjDp first; g_params, mu, nu and count are required");
     return SURJ_E_INVALID;
   }
-  if (plan->exec != 1 && plan->exec != 2) {
+  if (plan->exec != 1 && plan->exec != 2 && plan->exec != 4) {
     surj_set_error("the fused peer-memory exchange serves the fused executors; use an all-reduce for wide networks");
     return SURJ_E_UNSUPPORTED;
   }

@@ -19,10 +19,11 @@ struct SurjPlan {
   uint64_t key = 0;
   const SmallKernels* fused = nullptr;  // generation-1 fused kernel (per-chain generated code), if registered
   struct VmPlan* vmp = nullptr;         // generation-2 fused kernel (interpreter), if the chain fits
+  struct CcPlan* ccp = nullptr;         // compact looped kernel for affine coupling / funnel chains (compact.cuh)
   // lazily filled device facts
   mutable bool dev_ready = false;
   mutable int n_sm = 148, fwd_blocks = 4, bwd_blocks = 2;
-  int exec = 0;  // 1 generated straight-line kernel, 2 fused interpreter kernel, 3 per-op executor
+  int exec = 0;  // 1 generated straight-line kernel, 2 fused interpreter kernel, 3 per-op executor, 4 compact looped kernel
 };
 
 void surj_set_error(const std::string& msg);

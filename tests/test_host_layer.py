@@ -163,7 +163,7 @@ def test_smoke_shapes_of_reference_tests_compile():
     for batch in (dict(y=torch.zeros((10, dim))), dict(y=torch.zeros((10, dim)), x=torch.zeros((10, 2)))):
       traced, layout = hk.transform(fn2).trace(method="log_prob", **batch)
       plan = _runtime.get_plan(traced[0])
-      assert plan.executor in ("fused", "layered", "gen1"), name
+      assert plan.executor in ("fused", "layered", "gen1", "compact"), name
       assert plan.dim_in == dim
 
 
@@ -171,7 +171,7 @@ def test_every_baseline_config_compiles_to_a_plan():
   for name, c in configs.CONFIGS.items():
     spec = fused_chains.spec_of(c["make"](), c["dim"], c["dim_x"])
     plan = _runtime.get_plan(spec)
-    want = {"cfg1": "gen1", "cfg2": "gen1", "cfg3": "gen1", "cfg4": "layered", "cfg5": "layered", "mlpf": "fused", "cond": "fused"}[name]
+    want = {"cpl": "compact", "cfg1": "gen1", "cfg2": "gen1", "cfg3": "gen1", "cfg4": "layered", "cfg5": "layered", "mlpf": "fused", "cond": "fused"}[name]
     assert plan.executor == want, (name, plan.executor)
     assert plan.launches(False) >= 1 and plan.launches(True) >= 2
 
