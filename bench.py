@@ -24,6 +24,10 @@ import sys
 import threading
 import time
 
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line the contract asks for
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+  os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
