@@ -24,11 +24,8 @@ import sys
 import threading
 import time
 
-# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line the contract asks for
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-  os.environ["NCCL_DEBUG"] = "WARN"
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_RESULT_OUT = sys.stdout
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
@@ -116,7 +113,7 @@ def run_reference(args):
     "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "gpu_launches": 0,
   }
-  print(json.dumps(line), flush=True)
+  print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------- clock sampler
@@ -443,7 +440,7 @@ def run_b200(args):
       "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps * ts.launches_per_step(),
       "roofline": roofline, "cpu_baseline": cpu, "log_prob": logprob, "final_loss": loss_resident,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
   if world > 1:
     # CUDA graphs that captured NCCL collectives keep the communicator busy at teardown
     # (destroy_process_group was seen to hang); everything is measured and printed: leave hard.
@@ -455,6 +452,12 @@ def run_b200(args):
 
 
 def main():
+  # stdout carries exactly ONE line, the JSON result: everything libraries print there (NCCL's version banner, ...)
+  # is sent to stderr by pointing file descriptor 1 at stderr for the run and keeping the real stdout aside.
+  global _RESULT_OUT
+  sys.stdout.flush()
+  _RESULT_OUT = os.fdopen(os.dup(1), "w")
+  os.dup2(2, 1)
   args = parse()
   if args.impl == "reference":
     run_reference(args)

@@ -473,12 +473,11 @@ struct AdamArgs {
   float* params; float* mu; float* nu; int32_t* count;
   float lr, b1, b2, eps;
 };
-// Data-parallel exchange over NVLink peer memory (SurjDp): every rank owns a mailbox
-// box[2][world][npad] + flags[2][world][column blocks] that its peers write into directly.
+// Data-parallel exchange over NVLink peer memory (SurjDp): every rank owns a mailbox box[2][world][npad] of
+// 8-byte slots (float value | step tag << 32) that its peers write into directly.
 struct DpArgs {
-  float* const* peer_box;       // [world] device pointers to the peers' mailboxes (nullptr: single GPU)
-  unsigned* const* peer_flags;  // [world]
-  float* my_box; unsigned* my_flags;
+  unsigned long long* const* peer_box;  // [world] device pointers to the peers' mailboxes (nullptr: single GPU)
+  unsigned long long* my_box;
   int rank, world;
   int* err;                     // set to 1 if a peer did not arrive in time
 };
@@ -535,36 +534,34 @@ surj_reduce_partials_kernel(const float* __restrict__ partials, int nrows, int n
         for (int k = 0; k < RSL; ++k) g += __ldcg(slices + (size_t)k * npad + col);
       }
       if (multi) {
-        // Data parallel: this warp finishes its 32 columns across ALL ranks.  My shard's sums go straight
-        // into every rank's mailbox (NVLink peer stores), a per-column-block flag says "delivered", then the
-        // peers' contributions are summed in rank order (bit-identical on every rank) and Adam is applied.
-        const int t = *ad.count + 1, buf = t & 1;
+        // Data parallel: this warp finishes its 32 columns across ALL ranks.  My shard's sums go straight into every
+        // rank's mailbox (NVLink peer stores); value and step tag travel in ONE aligned 8-byte store, so a value is
+        // usable the moment it is visible (no fence + separate flag round trip).  The peers' contributions are summed
+        // in rank order (bit-identical on every rank) and Adam is applied.  The mailbox is double-buffered by step
+        // parity: a rank can be at most one step ahead of the slowest.
+        const unsigned t = (unsigned)(*ad.count + 1);
+        const int buf = (int)(t & 1u);
         if (valid) {
           const size_t slot = ((size_t)buf * dp.world + dp.rank) * npad + col;
-          for (int p = 0; p < dp.world; ++p) dp.peer_box[p][slot] = g;
-        }
-        __threadfence_system();
-        __syncwarp();
-        const size_t fslot = ((size_t)buf * dp.world) * gridDim.x + blockIdx.x;
-        for (int r = lane; r < dp.world; r += 32) {
-          volatile unsigned* f = dp.peer_flags[r] + fslot + (size_t)dp.rank * gridDim.x;
-          *f = (unsigned)t;  // rank `rank` has delivered column block blockIdx.x of step t
-        }
-        for (int r = lane; r < dp.world; r += 32) {
-          volatile unsigned* mine = dp.my_flags + fslot + (size_t)r * gridDim.x;
-          const long long t0 = clock64();
-          while (*mine != (unsigned)t) {
-            if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone; report instead of hanging the GPU
-              *dp.err = 1;
-              break;
+          const unsigned long long packed = ((unsigned long long)t << 32) | (unsigned long long)__float_as_uint(g);
+          for (int p = 0; p < dp.world; ++p) reinterpret_cast<volatile unsigned long long*>(dp.peer_box[p])[slot] = packed;
+          g = 0.0f;
+          for (int r = 0; r < dp.world; ++r) {
+            const volatile unsigned long long* src =
+              reinterpret_cast<const volatile unsigned long long*>(dp.my_box) + ((size_t)buf * dp.world + r) * npad + col;
+            unsigned long long v = *src;
+            const long long t0 = clock64();
+            while ((unsigned)(v >> 32) != t) {
+              if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone; report instead of hanging the GPU
+                *dp.err = 1;
+                break;
+              }
+              v = *src;
             }
+            g += __uint_as_float((unsigned)v);
           }
         }
-        __threadfence_system();
         __syncwarp();
-        g = 0.0f;
-        if (valid)
-          for (int r = 0; r < dp.world; ++r) g += __ldcg(dp.my_box + ((size_t)buf * dp.world + r) * npad + col);
       }
       if (valid) {
         if (col < np) {
@@ -750,18 +747,16 @@ extern "C" size_t surj_plan_forward_workspace_bytes(const SurjPlan* plan, int64_
 // Replicated parameters, sharded batch: the flat gradient (+ loss) of every rank must be summed before the
 // Adam update.  For the KB-sized gradients of the small-network configs an NCCL
 // all-reduce (launch + protocol latency) costs as much as a fifth of the step, so the exchange is fused into
-// the gradient-reduction kernel: each rank stores its reduced gradient directly into every peer's mailbox
-// (NVLink / NVSwitch peer memory), raises a flag, waits for the peers' flags, sums the mailbox in rank order
-// (bit-identical on all ranks) and applies Adam -- backward kernel + ONE kernel, no NCCL call in the step.
+// the gradient-reduction kernel: each rank stores its reduced gradient, tagged with the step number, directly into every
+// peer's mailbox (NVLink / NVSwitch peer memory), waits until the peers' tagged values have landed in its own, sums them in
+// rank order (bit-identical on all ranks) and applies Adam -- backward kernel + ONE kernel, no NCCL call in the step.
+typedef unsigned long long SurjSlot;  // float value | (step tag << 32)
 struct SurjDp {
   int rank = 0, world = 1, npad = 0;
-  float* box = nullptr;         // [2][world][npad]
-  unsigned* flags = nullptr;    // [2][world][column blocks], same allocation as box
-  std::vector<void*> opened;    // peers' mappings (cudaIpcOpenMemHandle)
-  float** d_peer_box = nullptr;
-  unsigned** d_peer_flags = nullptr;
+  SurjSlot* box = nullptr;       // [2][world][npad]
+  std::vector<void*> opened;     // peers' mappings (cudaIpcOpenMemHandle)
+  SurjSlot** d_peer_box = nullptr;
   int* d_err = nullptr;
-  size_t box_floats = 0;
 };
 
 extern "C" int surj_dp_create(int32_t rank, int32_t world, int64_t n_params, SurjDp** out, unsigned char* handle_out) {
@@ -772,15 +767,12 @@ extern "C" int surj_dp_create(int32_t rank, int32_t world, int64_t n_params, Sur
   SurjDp* d = new SurjDp();
   d->rank = rank; d->world = world;
   d->npad = (int)((n_params + 1 + 3) / 4 * 4);
-  d->box_floats = (size_t)2 * world * d->npad;
-  const size_t ncb = (size_t)(n_params + 1 + 31) / 32;
-  const size_t bytes = d->box_floats * 4 + (size_t)2 * world * ncb * 4 + 64;
+  const size_t bytes = (size_t)2 * world * d->npad * sizeof(SurjSlot);
   cudaError_t e = cudaMalloc((void**)&d->box, bytes);
-  if (e == cudaSuccess) e = cudaMemset(d->box, 0, bytes);
+  if (e == cudaSuccess) e = cudaMemset(d->box, 0, bytes);  // tag 0: no step has been delivered
   if (e == cudaSuccess) e = cudaMalloc((void**)&d->d_err, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(d->d_err, 0, sizeof(int));
   if (e != cudaSuccess) { delete d; return surj_cuda_fail(e, "surj_dp_create"); }
-  d->flags = (unsigned*)(d->box + d->box_floats);
   cudaIpcMemHandle_t h;
   e = cudaIpcGetMemHandle(&h, d->box);
   if (e != cudaSuccess) { delete d; return surj_cuda_fail(e, "cudaIpcGetMemHandle"); }
@@ -792,23 +784,19 @@ extern "C" int surj_dp_create(int32_t rank, int32_t world, int64_t n_params, Sur
 
 extern "C" int surj_dp_connect(SurjDp* d, const unsigned char* handles) {
   if (!d || !handles) { surj_set_error("surj_dp_connect: bad arguments"); return SURJ_E_INVALID; }
-  std::vector<float*> boxes(d->world);
-  std::vector<unsigned*> flags(d->world);
+  std::vector<SurjSlot*> boxes(d->world);
   for (int r = 0; r < d->world; ++r) {
-    if (r == d->rank) { boxes[r] = d->box; flags[r] = d->flags; continue; }
+    if (r == d->rank) { boxes[r] = d->box; continue; }
     cudaIpcMemHandle_t h;
     memcpy(&h, handles + (size_t)r * SURJ_IPC_HANDLE_BYTES, sizeof h);
     void* p = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) return surj_cuda_fail(e, "cudaIpcOpenMemHandle (peer mailbox)");
     d->opened.push_back(p);
-    boxes[r] = (float*)p;
-    flags[r] = (unsigned*)((float*)p + d->box_floats);
+    boxes[r] = (SurjSlot*)p;
   }
-  cudaError_t e = cudaMalloc((void**)&d->d_peer_box, sizeof(float*) * d->world);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d->d_peer_flags, sizeof(unsigned*) * d->world);
-  if (e == cudaSuccess) e = cudaMemcpy(d->d_peer_box, boxes.data(), sizeof(float*) * d->world, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d->d_peer_flags, flags.data(), sizeof(unsigned*) * d->world, cudaMemcpyHostToDevice);
+  cudaError_t e = cudaMalloc((void**)&d->d_peer_box, sizeof(SurjSlot*) * d->world);
+  if (e == cudaSuccess) e = cudaMemcpy(d->d_peer_box, boxes.data(), sizeof(SurjSlot*) * d->world, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return surj_cuda_fail(e, "surj_dp_connect");
   return SURJ_OK;
 }
@@ -817,7 +805,6 @@ extern "C" void surj_dp_destroy(SurjDp* d) {
   if (!d) return;
   for (void* p : d->opened) cudaIpcCloseMemHandle(p);
   if (d->d_peer_box) cudaFree(d->d_peer_box);
-  if (d->d_peer_flags) cudaFree(d->d_peer_flags);
   if (d->d_err) cudaFree(d->d_err);
   if (d->box) cudaFree(d->box);
   delete d;
@@ -847,7 +834,7 @@ extern "C" int surj_train_step_dp(const SurjPlan* plan, SurjDp* d, SurjStream st
     surj_set_error("SurjDp was created for a different parameter count");
     return SURJ_E_INVALID;
   }
-  DpArgs dp{d->d_peer_box, d->d_peer_flags, d->box, d->flags, d->rank, d->world, d->d_err};
+  DpArgs dp{d->d_peer_box, d->box, d->rank, d->world, d->d_err};
   return fused_backward(plan, (cudaStream_t)stream, y, x, params, nullptr, g_scale, nullptr, g_params, loss_out, nullptr,
                         nullptr, nullptr, workspace, workspace_bytes, batch, AdamArgs{params, mu, nu, count, lr, b1, b2, eps},
                         dp);
