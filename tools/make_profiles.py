@@ -84,12 +84,14 @@ Top warp stall reasons (warps stalled per issue-active cycle): {', '.join(f'{n} 
 
 Reading: DRAM traffic per launch = {rd / 1e6:.2f} MB read + {wr / 1e6:.2f} MB written vs 5.51 MB algorithmic
 (84 B/sample x 65536 + parameters): no re-reads, the kernel is not memory bound.  It is instruction-fetch / latency bound:
-`no_instruction` is the top stall (the straight-line stream is ~165 KB per CTA, SM instruction-cache hit rate
+`no_instruction` is the top stall (the straight-line stream is ~160 KB per warp, SM instruction-cache hit rate
 {d['sm__icc_request_hit_rate.pct'][0][:5]} %), 16 resident warps per SM (register-limited at 128), FMA pipe about a fifth active.
 History of this kernel in round 1 (CUDA-event time of kernel + reduction): 248 us (shared-memory float atomics in the gradient
 contraction) -> 92 us (shuffle-combined, atomics-free contraction) -> 62 us (register cap 128, 64-thread CTAs, 8 CTAs/SM;
 128/256/512-thread CTAs measured 79/118/145 us, 5-6 CTAs/SM 87 us) -> 59 us (one conditioner forward per layer in the backward)
--> 57 us (ticketed reduction with fused Adam) -> 53 us (approximate sigmoid for hidden activations only).
+-> 57 us (ticketed reduction with fused Adam) -> 53 us (approximate sigmoid for hidden activations only) -> 52 us
+(MUFU-only sigmoid, 6-instruction expf-grade exp).  See DESIGN.md section 2 for the instruction-delivery microbenchmarks and
+the two alternative kernels measured against this one.
 """)
   open(os.path.join(P, "r1_launch_lists.md"), "w").write(f"""# ncu launch lists (`--metrics gpu__time_duration.sum --clock-control none`), round 1
 
