@@ -75,3 +75,30 @@ def test_compact_z_gy_and_cotangents():
   for a, b, what in zip(res["compact"], res["fused"], ("z", "lp", "g_y", "g_params")):
     scale = max(1.0, float(b.abs().max()))
     assert float((a - b).abs().max()) <= 2e-5 * scale, what
+
+
+def test_compact_matches_generated_kernel_at_full_size():
+  """BASELINE batch and beyond (several tiles per CTA, ragged tail): log-probs and the summed gradient of the compact
+  kernel agree with the generated straight-line kernel, which is oracle-checked at oracle-sized batches."""
+  from surjectors_b200 import _runtime, configs, execution_mode, fused_chains
+
+  c = configs.CONFIGS["cfg2"]
+  spec = fused_chains.spec_of(c["make"](), c["dim"], 0)
+  dev = torch.device("cuda:0")
+  for B in (65536, 200003):
+    y = torch.randn((B, 20), generator=torch.Generator().manual_seed(B)).to(dev)
+    out = {}
+    for mode in ("compact", "gen1"):
+      with execution_mode(mode):
+        plan = _runtime.get_plan(spec)
+      assert plan.executor == mode
+      flat = (0.1 * torch.randn(plan.n_params, generator=torch.Generator().manual_seed(5))).to(dev)
+      _, lp = plan.fwd(y, None, flat, want_z=False)
+      gp, _, _, lp2 = plan.bwd(y, None, flat, g_scale=-1.0 / B, want_lp=True)
+      torch.cuda.synchronize()
+      assert torch.equal(lp, lp2)
+      out[mode] = (lp.cpu().double(), gp.cpu().double())
+    lp_a, gp_a = out["compact"]
+    lp_b, gp_b = out["gen1"]
+    assert float(((lp_a - lp_b).abs() / lp_b.abs().clamp(min=1.0)).max()) <= 1e-5
+    assert float((gp_a - gp_b).abs().max()) <= 1e-4 * float(gp_b.abs().max())
