@@ -7,6 +7,7 @@
 
 #include "compact.cuh"
 #include "compact.h"
+#include "compact_variants.h"
 #include "plan.h"
 
 namespace {
@@ -15,16 +16,17 @@ using cc::Layer;
 using cc::Mlp;
 using cc::Program;
 
-typedef void (*Kernel)(const Program, const cc::Io);
+using cc::Kernel;
+using cc::Variant;
 
-struct Variant {
-  int hc, hd, act;
-  Kernel fn;
-};
-#define CC_VARIANT(HC, HD, ACT) {HC, HD, ACT, &cc::chain_kernel<HC, HD, ACT>}
-#define CC_VARIANTS_FOR(ACT) \
-  CC_VARIANT(4, 4, ACT), CC_VARIANT(8, 4, ACT), CC_VARIANT(8, 8, ACT), CC_VARIANT(16, 8, ACT), CC_VARIANT(16, 16, ACT)
-const Variant kVariants[] = {CC_VARIANTS_FOR(surj::ACT_RELU), CC_VARIANTS_FOR(surj::ACT_SWISH), CC_VARIANTS_FOR(surj::ACT_TANH)};
+// the kernel instantiations live in compact_k{1,2,3}.cu (one activation each) so that they compile in parallel
+const Variant* find_variant(int hc, int hd, int act) {
+  const Variant* tabs[] = {cc::variants_relu(), cc::variants_swish(), cc::variants_tanh()};
+  for (const Variant* t : tabs)
+    for (int i = 0; i < cc::N_VARIANTS; ++i)
+      if (t[i].hc == hc && t[i].act == act && (hd == 0 || t[i].hd == hd)) return t + i;
+  return nullptr;
+}
 
 int pad4(int n) { return (n + 3) & ~3; }
 
@@ -75,9 +77,7 @@ CcPlan* cc_compile(const SurjPlan* plan, std::string* why) {
       hd = h;
     }
   }
-  const Variant* var = nullptr;
-  for (const Variant& v : kVariants)
-    if (v.hc == hc && v.act == act && (hd == 0 || v.hd == hd)) { var = &v; break; }
+  const Variant* var = find_variant(hc, hd, act);
   if (!var) { *why = "no compact kernel instantiated for these hidden widths / activation"; return nullptr; }
 
   CcPlan* c = new CcPlan();

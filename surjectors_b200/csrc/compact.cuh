@@ -197,7 +197,7 @@ CC_DEV void out_fwd(const Tile& t, const Mlp& m, const f2 (&h2)[H], int out0) {
 // adds the sums into sg.  The products run as packed FFMA2 over even / odd samples (an LDS.128 delivers two aligned
 // pairs of each operand).  Warps without a live item skip the job.
 // Not inlined: one copy of this loop nest serves every weight matrix.
-__device__ __noinline__ void contract_job(const Job* jp, float* rows, float* sg, const int* itab, int T, int tid, int nt) {
+static __device__ __noinline__ void contract_job(const Job* jp, float* rows, float* sg, const int* itab, int T, int tid, int nt) {
   constexpr int TA = 2, TG = 4;
   const Job j = *jp;
   const int KS = 1 << j.log2ks, KLEN = T >> j.log2ks;
