@@ -2,7 +2,7 @@
 //
 // Same program, same row layout ([row][sample], samples contiguous) as the fused interpreter
 // (vm.cuh), but the rows of a *chunk* of C samples live in the caller's workspace in global memory
-// (mostly L2-resident between kernels for C = 16384) and every matrix product is its own tiled
+// (C up to 131072 samples: wide enough to fill the GPU with the per-sample kernels) and every matrix product is its own tiled
 // FP32 kernel:
 //   vg_linear  out[j][s] = act(b[j] + sum_i W[i][j] in[i][s])        M = samples, N = outputs, K = inputs
 //   vg_dw      grad[i][j] += sum_s in[i][s] g[j][s]  (+ bias row)      contraction over the samples
@@ -228,9 +228,12 @@ vg_writeback(const int32_t* __restrict__ grad_dst, const int32_t* __restrict__ g
 namespace {
 inline size_t a256(size_t n) { return (n + 255) & ~(size_t)255; }
 inline int chunk_cols(int64_t B, int n_rows) {
-  // rows of one chunk must stay within ~1.5 GB and, when possible, L2-friendly (16384 samples)
-  int64_t c = std::min<int64_t>(16384, (B + 127) / 128 * 128);
-  const int64_t cap = ((int64_t)1536 << 20) / ((int64_t)n_rows * 4) / 128 * 128;
+  // rows of one chunk must stay within 8 GB; the target width trades L2 residency between kernels (small chunks)
+  // against resident threads in the per-sample kernels and grid sizes of the tiles (large chunks).  Measured at batch
+  // 262144 (cfg4 / cfg5 train step, ms): 16384: 629 / 729, 65536: 515 / 494, 131072: 499 / 474, 262144: 499 / 463.
+  static const int64_t target = [] { const char* e = getenv("SURJ_B200_CHUNK"); return e ? atoll(e) : 131072ll; }();
+  int64_t c = std::min<int64_t>(target, (B + 127) / 128 * 128);
+  const int64_t cap = ((int64_t)8192 << 20) / ((int64_t)n_rows * 4) / 128 * 128;
   c = std::max<int64_t>(128, std::min(c, cap));
   return (int)c;
 }
