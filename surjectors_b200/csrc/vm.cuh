@@ -36,6 +36,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace vm {
 
 enum : int32_t {
@@ -143,6 +145,25 @@ VM_DEV float act_bwd(int act, float a, float g) {
     }
     case ACT_ELU: return a > 0.0f ? g : g * expf(a);
     default: return a > 0.0f ? g : 0.01f * g;
+  }
+}
+
+// Runs f(std::integral_constant<int, ACT>{}) for the runtime activation code `act`.  Epilogues that apply an activation to
+// an unrolled register tile call this ONCE around the loop: each activation gets its own compact copy of the loop,
+// instead of the whole switch (tanhf, expm1f, ... inlined) being repeated per element -- that repetition made
+// vg_linear_tc 285 KB of code, most of it executed once per CTA at the cold instruction-fetch rate.
+template <class F>
+VM_DEV void with_act(int act, F&& f) {
+  switch (act) {
+    case ACT_IDENTITY: f(std::integral_constant<int, ACT_IDENTITY>{}); break;
+    case ACT_RELU: f(std::integral_constant<int, ACT_RELU>{}); break;
+    case ACT_SWISH: f(std::integral_constant<int, ACT_SWISH>{}); break;
+    case ACT_TANH: f(std::integral_constant<int, ACT_TANH>{}); break;
+    case ACT_SIGMOID: f(std::integral_constant<int, ACT_SIGMOID>{}); break;
+    case ACT_SOFTPLUS: f(std::integral_constant<int, ACT_SOFTPLUS>{}); break;
+    case ACT_GELU: f(std::integral_constant<int, ACT_GELU>{}); break;
+    case ACT_ELU: f(std::integral_constant<int, ACT_ELU>{}); break;
+    default: f(std::integral_constant<int, ACT_LEAKY_RELU>{}); break;
   }
 }
 

@@ -129,24 +129,27 @@ vg_linear(Op op, float* __restrict__ rows, int C, const float* __restrict__ par)
     }
   }
   const int acc_row = pre_row >= 0 ? pre_row : out_row;
+  with_act(act, [&](auto tag) {
+    constexpr int ACT = decltype(tag)::value;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int j = j0 + 4 * ty + q;
-    if (j >= n_out) continue;
-    const float b = b_off >= 0 ? par[b_off + j] : 0.0f;
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + 4 * ty + q;
+      if (j >= n_out) continue;
+      const float b = b_off >= 0 ? par[b_off + j] : 0.0f;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const size_t col = (size_t)s0 + 64 * h + 4 * tx;
-      float v[4] = {acc[q][4 * h] + b, acc[q][4 * h + 1] + b, acc[q][4 * h + 2] + b, acc[q][4 * h + 3] + b};
-      if (accumulate) {
-        const float4 p = *reinterpret_cast<const float4*>(rows + (size_t)(acc_row + j) * C + col);
-        v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
+      for (int h = 0; h < 2; ++h) {
+        const size_t col = (size_t)s0 + 64 * h + 4 * tx;
+        float v[4] = {acc[q][4 * h] + b, acc[q][4 * h + 1] + b, acc[q][4 * h + 2] + b, acc[q][4 * h + 3] + b};
+        if (accumulate) {
+          const float4 p = *reinterpret_cast<const float4*>(rows + (size_t)(acc_row + j) * C + col);
+          v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
+        }
+        if (pre_row >= 0) *reinterpret_cast<float4*>(rows + (size_t)(pre_row + j) * C + col) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(rows + (size_t)(out_row + j) * C + col) =
+            make_float4(act_fwd(ACT, v[0]), act_fwd(ACT, v[1]), act_fwd(ACT, v[2]), act_fwd(ACT, v[3]));
       }
-      if (pre_row >= 0) *reinterpret_cast<float4*>(rows + (size_t)(pre_row + j) * C + col) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(rows + (size_t)(out_row + j) * C + col) =
-          make_float4(act_fwd(act, v[0]), act_fwd(act, v[1]), act_fwd(act, v[2]), act_fwd(act, v[3]));
     }
-  }
+  });
 }
 
 // ---- grad[w_off + i*ld + j] += sum_s in[i][s] g[j][s]; grad[b_off + j] += sum_s g[j][s] (ones row).

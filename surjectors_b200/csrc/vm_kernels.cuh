@@ -42,14 +42,17 @@ VM_DEV void linear_chunks(Ctx<NT, S>& c, const float* __restrict__ par, const Op
         for (int q = 0; q < CH; ++q) acc[s][q] = fmaf(a, wv[q], acc[s][q]);
       }
     }
+    with_act(act, [&](auto tag) {
+      constexpr int ACT = decltype(tag)::value;
 #pragma unroll
-    for (int q = 0; q < CH; ++q)
+      for (int q = 0; q < CH; ++q)
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        const float v = acc[s][q];
-        if (pre_row >= 0) c.row(pre_row + j0 + q)[s * NT] = v;
-        c.row(out_row + j0 + q)[s * NT] = act_fwd(act, v);
-      }
+        for (int s = 0; s < S; ++s) {
+          const float v = acc[s][q];
+          if (pre_row >= 0) c.row(pre_row + j0 + q)[s * NT] = v;
+          c.row(out_row + j0 + q)[s * NT] = act_fwd(ACT, v);
+        }
+    });
   }
 }
 

@@ -319,16 +319,19 @@ vg_linear_tc(vm::Op op, float* __restrict__ rows, int C, const float* __restrict
   // epilogue: this thread holds sample s0 + lane_base + lane (its TMEM lane); acc[c] = output j0 + col0 + c
   const size_t col = (size_t)s0 + lane_base + lane;
   const int acc_row = pre_row >= 0 ? pre_row : out_row;
+  vm::with_act(act, [&](auto tag) {
+    constexpr int ACT = decltype(tag)::value;
 #pragma unroll
-  for (int c = 0; c < NCOL; ++c) {
-    const int j = j0 + col0 + c;
-    if (col0 + c < n_valid) {
-      float x = acc[c] + (b_off >= 0 ? __ldg(par + b_off + j) : 0.0f);
-      if (accumulate) x += rows[(size_t)(acc_row + j) * C + col];
-      if (pre_row >= 0) rows[(size_t)(pre_row + j) * C + col] = x;
-      rows[(size_t)(out_row + j) * C + col] = vm::act_fwd(act, x);
+    for (int c = 0; c < NCOL; ++c) {
+      const int j = j0 + col0 + c;
+      if (col0 + c < n_valid) {
+        float x = acc[c] + (b_off >= 0 ? __ldg(par + b_off + j) : 0.0f);
+        if (accumulate) x += rows[(size_t)(acc_row + j) * C + col];
+        if (pre_row >= 0) rows[(size_t)(pre_row + j) * C + col] = x;
+        rows[(size_t)(out_row + j) * C + col] = vm::act_fwd(ACT, x);
+      }
     }
-  }
+  });
   tmem_free(tmem_d, warp);
 }
 
@@ -542,16 +545,19 @@ vg_linear_pipe(vm::Op op, float* __restrict__ rows, int C, const float* __restri
     }
     const size_t col = (size_t)s0 + lane_base + lane;
     const int acc_row = pre_row >= 0 ? pre_row : out_row;
+    vm::with_act(act, [&](auto tag) {
+      constexpr int ACT = decltype(tag)::value;
 #pragma unroll
-    for (int c = 0; c < TN; ++c) {
-      const int j = j0 + c;
-      if (c < n_valid) {
-        float x = acc[c] + (b_off >= 0 ? __ldg(par + b_off + j) : 0.0f);
-        if (accumulate) x += rows[(size_t)(acc_row + j) * C + col];
-        if (pre_row >= 0) rows[(size_t)(pre_row + j) * C + col] = x;
-        rows[(size_t)(out_row + j) * C + col] = vm::act_fwd(act, x);
+      for (int c = 0; c < TN; ++c) {
+        const int j = j0 + c;
+        if (c < n_valid) {
+          float x = acc[c] + (b_off >= 0 ? __ldg(par + b_off + j) : 0.0f);
+          if (accumulate) x += rows[(size_t)(acc_row + j) * C + col];
+          if (pre_row >= 0) rows[(size_t)(pre_row + j) * C + col] = x;
+          rows[(size_t)(out_row + j) * C + col] = vm::act_fwd(ACT, x);
+        }
       }
-    }
+    });
   }
   tc_fence_before();
   __syncthreads();
