@@ -281,7 +281,7 @@ Carve carve(const VmPlan* v, void* ws, int C, int prog) {
   k.scal_g = take(std::max(v->n_scalars, 1));
   k.loss = take(1);
   k.rows = take((size_t)v->n_rows * C);
-  static const bool pipe_mode = [] { const char* e = getenv("SURJ_B200_TC"); return e && atoi(e) == 5; }();
+  static const bool pipe_mode = [] { const char* e = getenv("SURJ_B200_TC"); return !e || atoi(e) == 5; }();
   const VmTcInfo& t = tc_info(v, prog);
   k.w_tiles = take(pipe_mode ? std::max<size_t>(t.w_floats, 1) : 1);
   k.a_tiles = take(pipe_mode ? std::max<size_t>((size_t)t.max_kpad * 2 * C, 1) : 1);
@@ -320,8 +320,10 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   const int C = chunk_cols(B, v->n_rows);
   Carve k = carve(v, ws, C, prog);
   static const int tc_mode = [] {
-    const char* e = getenv("SURJ_B200_TC");  // 0: FP32 SIMT tiles only; 2: tcgen05 for LINEAR only; 3: for LINEAR_DW only; 5: pipelined LINEAR
-    return e ? atoi(e) : 1;
+    // 5 (default): TMA-fed pipelined tcgen05 LINEAR + tcgen05 LINEAR_DW; 1: register-staged tcgen05 for both;
+    // 2 / 3: register-staged tcgen05 for LINEAR / LINEAR_DW only; 0: FP32 SIMT tiles only
+    const char* e = getenv("SURJ_B200_TC");
+    return e ? atoi(e) : 5;
   }();
   const bool use_tc_lin = tc_mode == 1 || tc_mode == 2 || tc_mode == 5, use_tc_dw = tc_mode == 1 || tc_mode == 3 || tc_mode == 5;
   static const bool use_tc = [] {
@@ -352,9 +354,10 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
     vm::vg_scalars<<<((int)v->sjobs.size() + 31) / 32, 32, 0, st>>>(P.sjobs, (int)v->sjobs.size(), k.par, k.scal);
   // tensor-core LINEAR ops: split (hi / lo TF32) and tile every weight matrix they use, once per call
   const VmTcInfo& tci = tc_info(v, prog);
-  // SURJ_B200_TC=5: the TMA-fed pipelined kernel on pre-tiled operands.  Measured (profiles/r1_linear_pipe_ncu.md): it is
-  // L2-bandwidth bound (hi + lo planes of both operands stream per 128x128 tile: 16 FLOP/B) and ends up slower than the
-  // register-staged kernel, which reads each fp32 operand once; it stays opt-in until tiles are shared across a cluster.
+  // Default: the TMA-fed pipelined kernel on pre-tiled operands.  It is L2-bandwidth bound (hi + lo planes of both
+  // operands stream per 128x128 tile: 16 FLOP/B, profiles/r1_linear_pipe_ncu.md) but issues ~10x fewer instructions than
+  // the register-staged kernel (SURJ_B200_TC=1), whose in-CTA split / staging is ALU-bound: measured at batch 262144,
+  // train step cfg4 357 vs 413 ms, cfg5 349 vs 381 ms; log_prob 78 vs 100 and 73 vs 84 ms.
   const bool pipe = use_tc && tc_mode == 5;
   if (pipe) {
     std::map<long long, bool> done;
