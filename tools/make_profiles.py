@@ -105,13 +105,18 @@ Per-launch times under ncu are cold-cache and serialised: compare SHARES, not ab
 stage of the reduction); `chain_fwd_kernel` is the log_prob-only measurement of the same run.  `bench.py` measures the
 step pair live with CUDA events (see r1_bench_n1.json: `roofline.us_per_launch`).
 
-## `python tools/bench_wide.py --config cfg4 --batch 32768 --reps 1`, first tcgen05 version (r1_cfg4_launches_tc1_ncu.csv)
+## `python tools/bench_wide.py --config cfg4 --batch 131072 --reps 1` (per-op executor, defaults; r1_cfg4_launches_ncu.csv)
 
-{launch_summary(os.path.join(P, 'r1_cfg4_launches_tc1_ncu.csv'))}
+{launch_summary(os.path.join(P, 'r1_cfg4_launches_ncu.csv'))}
 
-## same, FP32 SIMT tiles only (`SURJ_B200_TC=0`, r1_cfg4_launches_tc0_ncu.csv)
+## `python tools/bench_wide.py --config cfg5 --batch 131072 --reps 1` (r1_cfg5_launches_ncu.csv)
 
-{launch_summary(os.path.join(P, 'r1_cfg4_launches_tc0_ncu.csv'))}
+{launch_summary(os.path.join(P, 'r1_cfg5_launches_ncu.csv'))}
+
+`vg_linear_pipe` = TMA-fed pipelined tcgen05 LINEAR on operand planes tiled by `vg_tile`; `vg_dw_tc` = register-staged
+tcgen05 weight-gradient contraction; `vg_elem` = fused runs of per-sample ops (splines, affine, gathers, activations'
+derivatives); `vg_linear` / `vg_dw` = FP32 SIMT tiles for operands narrower than 32.  Earlier in the round, with the
+register-staged LINEAR and 16 384-sample chunks, the shares for cfg4 were `vg_linear_tc` 54 %, `vg_dw_tc` 31 %, `vg_elem` 13 %.
 """)
   print(open(os.path.join(P, "r1_cfg2_bwd_ncu.md")).read())
 
