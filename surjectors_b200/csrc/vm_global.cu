@@ -262,6 +262,45 @@ const VmTcInfo& tc_info(const VmPlan* v, int prog) {
     t.w_off[i] = it->second;
     t.max_kpad = std::max(t.max_kpad, nkb * vmtc::PBK);
   }
+  // structural zeros at tile granularity, read off the gather table (masked weights are STAGE_ZERO)
+  t.kr.assign(ops.size(), VmKRange{});
+  t.dw_skip.assign(ops.size(), 0ull);
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const vm::Op& op = ops[i];
+    if (tc_linear_op(op)) {
+      const int n_in = op.a[1], n_real = op.a[12], tw = op.a[10], ld = op.a[11];
+      const int n_tiles = (op.a[5] + vmtc::TN - 1) / vmtc::TN, nkb = (n_in + vmtc::PBK - 1) / vmtc::PBK;
+      if (n_tiles > 8 || nkb > 65535) continue;
+      VmKRange r{};
+      r.enabled = 1;
+      for (int tl = 0; tl < n_tiles; ++tl) {
+        int kmin = n_in, kmax = -1;
+        for (int j = tl * vmtc::TN; j < std::min(n_real, (tl + 1) * vmtc::TN); ++j)
+          for (int kk = 0; kk < n_in; ++kk)
+            if (v->stage[(size_t)tw + (size_t)j * ld + kk] != vm::STAGE_ZERO) { kmin = std::min(kmin, kk); kmax = std::max(kmax, kk); }
+        r.lo[tl] = (unsigned short)(kmax < 0 ? 0 : kmin / vmtc::PBK);
+        r.hi[tl] = (unsigned short)(kmax < 0 ? 0 : kmax / vmtc::PBK + 1);
+      }
+      t.kr[i] = r;
+    } else if (op.code == vm::OP_LINEAR_DW) {
+      const int n_in = op.a[1], n_out = op.a[3], w_off = op.a[4], ld = op.a[5];
+      const int NA = n_in + (op.a[6] >= 0 ? 1 : 0);
+      const int ti = (NA + vmtc::TM - 1) / vmtc::TM, tj = (n_out + vmtc::TN - 1) / vmtc::TN;
+      if (ti * tj > 64) continue;
+      unsigned long long skip = 0;
+      for (int a = 0; a < ti; ++a)
+        for (int b = 0; b < tj; ++b) {
+          bool any = false;
+          for (int ii = a * vmtc::TM; ii < std::min(NA, (a + 1) * vmtc::TM) && !any; ++ii) {
+            if (ii >= n_in) { any = true; break; }  // the ones row (bias gradient)
+            for (int j = b * vmtc::TN; j < std::min(n_out, (b + 1) * vmtc::TN); ++j)
+              if (v->stage[(size_t)w_off + (size_t)ii * ld + j] != vm::STAGE_ZERO) { any = true; break; }
+          }
+          if (!any) skip |= 1ull << (a * tj + b);
+        }
+      t.dw_skip[i] = skip;
+    }
+  }
   t.ready = true;
   return t;
 }
@@ -383,7 +422,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
                                                                                        cols, op.a[1], nkb, k.a_tiles);
           dim3 grid(cols / vmtc::TM, (op.a[5] + vmtc::TN - 1) / vmtc::TN);
           vmtc::vg_linear_pipe<<<grid, vmtc::PIPE_THREADS, vmtc::PIPE_SMEM, st>>>(op, k.rows, C, k.par, k.a_tiles,
-                                                                                 k.w_tiles + tci.w_off[pc], nkb);
+                                                                                 k.w_tiles + tci.w_off[pc], nkb, tci.kr[pc]);
         } else if (use_tc && use_tc_lin && tc_linear_op(op)) {  // register-staged tcgen05 kernel
           dim3 grid(cols / vmtc::TM, (op.a[5] + vmtc::TN - 1) / vmtc::TN);
           vmtc::vg_linear_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, k.par);
@@ -400,7 +439,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           const int want = std::max(1, (592 + tiles - 1) / tiles);
           const int slab = std::max(512, (cols / want) / 128 * 128);
           dim3 grid((NA + vmtc::TM - 1) / vmtc::TM, (NG + vmtc::TN - 1) / vmtc::TN, (cols + slab - 1) / slab);
-          vmtc::vg_dw_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, cols, slab, k.grad);
+          vmtc::vg_dw_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, cols, slab, k.grad, tci.dw_skip[pc]);
         } else {
           const int slab = 2048;
           dim3 grid((NA + vm::DBI - 1) / vm::DBI, (NG + vm::DBJ - 1) / vm::DBJ, (cols + slab - 1) / slab);

@@ -7,8 +7,17 @@
 #include "vm.cuh"
 
 // Which OP_LINEAR ops of a program run on the pipelined tcgen05 kernel and where their tiled weight copy lives
+// Structural zeros of a staged weight matrix at tile granularity (masked MADE weights are STAGE_ZERO in the gather table):
+// K-block range [lo, hi) that can contribute to each 128-output tile of a LINEAR, and the all-zero 128x128 tiles of a
+// LINEAR_DW.  Passed to the kernels by value; matrices with more tiles than fit simply run dense.
+struct VmKRange {
+  unsigned short lo[8], hi[8];
+  int enabled;
+};
 struct VmTcInfo {
   bool ready = false;
+  std::vector<VmKRange> kr;                // per op (LINEAR on the pipelined kernel)
+  std::vector<unsigned long long> dw_skip; // per op (LINEAR_DW): bit (i_tile * n_j_tiles + j_tile) set = all-zero tile
   std::vector<long long> w_off;  // per op: float offset of its tiled [out][in] weights inside the weight-tile region, -1 = not a tensor-core op
   size_t w_floats = 0;           // size of the weight-tile region
   int max_kpad = 0;              // max over tensor-core ops of n_in rounded up to 32 (activation tiles need kpad * 2 floats per sample)

@@ -28,6 +28,7 @@
 #include <stdint.h>
 
 #include "vm.cuh"
+#include "vm_plan.h"
 
 namespace vmtc {
 
@@ -337,7 +338,9 @@ vg_linear_tc(vm::Op op, float* __restrict__ rows, int C, const float* __restrict
 
 // ---- LINEAR_DW: grid (ceil(NA / 128), ceil(n_out / 128), slabs); 256 threads; K = samples of the slab.
 __global__ void __launch_bounds__(NTHR, 2)
-vg_dw_tc(vm::Op op, const float* __restrict__ rows, int C, int cols, int slab, float* __restrict__ grad) {
+vg_dw_tc(vm::Op op, const float* __restrict__ rows, int C, int cols, int slab, float* __restrict__ grad,
+         unsigned long long skip_tiles) {
+  if ((skip_tiles >> (blockIdx.x * gridDim.y + blockIdx.y)) & 1ull) return;  // every weight of this tile is masked: exact-zero gradient
   extern __shared__ unsigned char smem_raw[];
   const Smem sm = carve(smem_raw);
   const int in_row = op.a[0], n_in = op.a[1], g_row = op.a[2], n_out = op.a[3], w_off = op.a[4], ld = op.a[5],
@@ -453,7 +456,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // grid (sample tiles, output tiles); op fields as OP_LINEAR (a5 = padded outputs, a12 = real outputs).
 __global__ void __launch_bounds__(PIPE_THREADS, 2)
 vg_linear_pipe(vm::Op op, float* __restrict__ rows, int C, const float* __restrict__ par, const float* __restrict__ a_tiles,
-               const float* __restrict__ b_tiles, int nkb) {
+               const float* __restrict__ b_tiles, int nkb, VmKRange kr) {
   extern __shared__ unsigned char smem_raw[];
   uintptr_t base = ((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023;
   float* stage_mem = (float*)base;  // [PIPE_STAGES][A block | B block]
@@ -468,6 +471,9 @@ vg_linear_pipe(vm::Op op, float* __restrict__ rows, int C, const float* __restri
   const int s0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
   const int n_valid = min(TN, n_out - j0);
   const int n_tile = (n_valid + 15) & ~15;
+  // K blocks that can contribute to this output tile (structural zeros of the weights skipped at tile granularity)
+  const int kb0 = kr.enabled ? (int)kr.lo[blockIdx.y] : 0;
+  const int nk = (kr.enabled ? (int)kr.hi[blockIdx.y] : nkb) - kb0;
   if (tid == 0) {
     for (int s = 0; s < PIPE_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 4); }
@@ -488,20 +494,20 @@ vg_linear_pipe(vm::Op op, float* __restrict__ rows, int C, const float* __restri
     if (lane == 0) {  // ---- producer
       const float* a_src = a_tiles + (size_t)blockIdx.x * nkb * BLOCK_FLOATS;
       const float* b_src = b_tiles + (size_t)blockIdx.y * nkb * BLOCK_FLOATS;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % PIPE_STAGES;
         if (kb >= PIPE_STAGES) mbar_wait(empty + s, ((kb / PIPE_STAGES) - 1) & 1);
         float* sa = stage_mem + (size_t)s * 2 * BLOCK_FLOATS;
         mbar_expect_tx(full + s, 2 * BLOCK_FLOATS * 4);
-        bulk_g2s(sa, a_src + (size_t)kb * BLOCK_FLOATS, BLOCK_FLOATS * 4, full + s);
-        bulk_g2s(sa + BLOCK_FLOATS, b_src + (size_t)kb * BLOCK_FLOATS, BLOCK_FLOATS * 4, full + s);
+        bulk_g2s(sa, a_src + (size_t)(kb0 + kb) * BLOCK_FLOATS, BLOCK_FLOATS * 4, full + s);
+        bulk_g2s(sa + BLOCK_FLOATS, b_src + (size_t)(kb0 + kb) * BLOCK_FLOATS, BLOCK_FLOATS * 4, full + s);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---- MMA issuer
       const uint32_t idesc =
           (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % PIPE_STAGES, buf = kb & 1;
         mbar_wait(full + s, (kb / PIPE_STAGES) & 1);
         if (kb >= 2) mbar_wait(tmem_empty + buf, ((kb >> 1) - 1) & 1);
@@ -526,7 +532,7 @@ vg_linear_pipe(vm::Op op, float* __restrict__ rows, int C, const float* __restri
     float acc[TN];
 #pragma unroll
     for (int c = 0; c < TN; ++c) acc[c] = 0.0f;
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = 0; kb < nk; ++kb) {
       const int buf = kb & 1;
       mbar_wait(tmem_full + buf, (kb >> 1) & 1);
       tc_fence_after();
