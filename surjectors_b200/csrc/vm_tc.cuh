@@ -5,7 +5,7 @@
 // issued as tcgen05.mma.cta_group::1.kind::tf32 by ONE thread, operands in shared memory in the
 // canonical K-major no-swizzle ("interleave") UMMA layout, accumulator in TMEM, read back with
 // tcgen05.ld for the epilogue.  Every fp32 operand x is split into hi = tf32(x) and
-// lo = tf32(x - hi) while it is staged, and each K step issues lo*hi + hi*lo + hi*hi, which keeps the
+// lo = x - hi (truncated to tf32 by the tensor core itself), and each K step issues lo*hi + hi*lo + hi*hi, which keeps the
 // product error near 2^-21 relative -- the 1e-5 / 1e-4 parity bounds rule out plain TF32 (2^-11).
 // The tensor core's accumulator add truncates, which shows up as a systematic bias once hundreds
 // of K steps are chained (measured: 1.7e-5 on the 16-layer MADE config); so only ONE K block (32) is
@@ -42,11 +42,12 @@ constexpr int TMEM_COLS = 2 * TN;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// hi = x rounded to TF32 (10 mantissa bits, round-half-away: add half an ulp, clear the 13 low bits); the PTX
+// cvt.rna.tf32.f32 compiles to the same two integer ops plus an inf / NaN guard (FSETP + SEL) that adds nothing here
+// (the mask leaves inf as inf, NaN as NaN).  lo = x - hi is exact and is handed to the tensor core as it is: kind::tf32
+// ignores the 13 low mantissa bits of its inputs, i.e. truncates lo, which leaves the 3xTF32 product error at 2^-21.
+// Split cost: 3 instructions per element instead of 9.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 __device__ __forceinline__ int tile_off(int r, int k) {  // float offset of element (r, k) inside an operand tile
   return (r >> 3) * 256 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
@@ -129,8 +130,8 @@ constexpr int NCOL = TN / 2;  // accumulator columns per thread
 // split-store 4 consecutive-k values of row r into the hi / lo tiles (one 16-byte core-matrix row each)
 __device__ __forceinline__ void put4(float* hi, float* lo, int r, int k, float4 v) {
   float4 h, l;
-  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-  l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+  h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
   const int o = tile_off(r, k);
   *reinterpret_cast<float4*>(hi + o) = h;
   *reinterpret_cast<float4*>(lo + o) = l;
@@ -430,8 +431,8 @@ vg_tile(const float* __restrict__ src, size_t pitch, int n_rows, int K, int nkb,
       }
     }
     float4 h, l;
-    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
     float* blk = dst + ((size_t)rt * nkb + kb) * BLOCK_FLOATS;
     const int o = ptile_off(r, k0 - kb * PBK);
     *reinterpret_cast<float4*>(blk + o) = h;
