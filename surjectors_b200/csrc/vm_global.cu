@@ -284,15 +284,13 @@ const VmTcInfo& tc_info(const VmPlan* v, int prog) {
       t.kr[i] = r;
     } else if (op.code == vm::OP_LINEAR_DW) {
       const int n_in = op.a[1], n_out = op.a[3], w_off = op.a[4], ld = op.a[5];
-      const int NA = n_in + (op.a[6] >= 0 ? 1 : 0);
-      const int ti = (NA + vmtc::TM - 1) / vmtc::TM, tj = (n_out + vmtc::TN - 1) / vmtc::TN;
+      const int ti = (n_in + vmtc::TM - 1) / vmtc::TM, tj = (n_out + vmtc::TN - 1) / vmtc::TN;
       if (ti * tj > 64) continue;
       unsigned long long skip = 0;
       for (int a = 0; a < ti; ++a)
         for (int b = 0; b < tj; ++b) {
           bool any = false;
-          for (int ii = a * vmtc::TM; ii < std::min(NA, (a + 1) * vmtc::TM) && !any; ++ii) {
-            if (ii >= n_in) { any = true; break; }  // the ones row (bias gradient)
+          for (int ii = a * vmtc::TM; ii < std::min(n_in, (a + 1) * vmtc::TM) && !any; ++ii) {
             for (int j = b * vmtc::TN; j < std::min(n_out, (b + 1) * vmtc::TN); ++j)
               if (v->stage[(size_t)w_off + (size_t)ii * ld + j] != vm::STAGE_ZERO) { any = true; break; }
           }
@@ -435,10 +433,12 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
         const int NA = op.a[1] + (op.a[6] >= 0 ? 1 : 0), NG = op.a[3];
         if (use_tc && use_tc_dw && NA >= 32 && NG >= 32) {
           // sample slabs sized so the grid fills the machine about twice (2 CTAs per SM x 148 SMs x 2)
-          const int tiles = ((NA + vmtc::TM - 1) / vmtc::TM) * ((NG + vmtc::TN - 1) / vmtc::TN);
+          // (the bias gradient comes out of staging the g operand, so the tile rows cover the n_in real inputs only)
+          const int ti = (op.a[1] + vmtc::TM - 1) / vmtc::TM;
+          const int tiles = ti * ((NG + vmtc::TN - 1) / vmtc::TN);
           const int want = std::max(1, (592 + tiles - 1) / tiles);
           const int slab = std::max(512, (cols / want) / 128 * 128);
-          dim3 grid((NA + vmtc::TM - 1) / vmtc::TM, (NG + vmtc::TN - 1) / vmtc::TN, (cols + slab - 1) / slab);
+          dim3 grid(ti, (NG + vmtc::TN - 1) / vmtc::TN, (cols + slab - 1) / slab);
           vmtc::vg_dw_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, cols, slab, k.grad, tci.dw_skip[pc]);
         } else {
           const int slab = 2048;

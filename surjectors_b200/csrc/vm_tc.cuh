@@ -145,6 +145,8 @@ __device__ __forceinline__ void put4(float* hi, float* lo, int r, int k, float4 
 struct LoadKMajor {
   const float* src; size_t pitch; int tile_rows, n_valid_rows, special_row; const float* special_src;
   float4 v[4];
+  float rs[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // running sum over K of this thread's part of its four rows (row = row_of(tid, it))
+  __device__ __forceinline__ static int row_of(int tid, int it) { const int idx = tid + it * NTHR; return (idx & 7) + 8 * (idx >> 6); }
   __device__ __forceinline__ void load(int k0, int k_valid, int tid) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -161,6 +163,7 @@ struct LoadKMajor {
         }
       }
       v[it] = t;
+      rs[it] += (t.x + t.y) + (t.z + t.w);
     }
   }
   __device__ __forceinline__ void store(float* hi, float* lo, int tid) const {
@@ -337,35 +340,55 @@ vg_linear_tc(vm::Op op, float* __restrict__ rows, int C, const float* __restrict
   tmem_free(tmem_d, warp);
 }
 
-// ---- LINEAR_DW: grid (ceil(NA / 128), ceil(n_out / 128), slabs); 256 threads; K = samples of the slab.
+// ---- LINEAR_DW: grid (ceil(n_in / 128), ceil(n_out / 128), slabs); 256 threads; K = samples of the slab.
+// grad[w] += in^T g over the slab.  The bias gradient (column sums of g) is NOT a 129th / 257th / 513th operand row --
+// that would add a whole extra tile row re-reading all of g -- but falls out of staging the g operand: every thread
+// keeps the running sums of the g values it loads, and the CTAs of tile row 0 add them to grad[b].
 __global__ void __launch_bounds__(NTHR, 2)
 vg_dw_tc(vm::Op op, const float* __restrict__ rows, int C, int cols, int slab, float* __restrict__ grad,
          unsigned long long skip_tiles) {
-  if ((skip_tiles >> (blockIdx.x * gridDim.y + blockIdx.y)) & 1ull) return;  // every weight of this tile is masked: exact-zero gradient
   extern __shared__ unsigned char smem_raw[];
   const Smem sm = carve(smem_raw);
   const int in_row = op.a[0], n_in = op.a[1], g_row = op.a[2], n_out = op.a[3], w_off = op.a[4], ld = op.a[5],
             b_off = op.a[6];
-  const int NA = n_in + (b_off >= 0 ? 1 : 0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
   const int s_begin = blockIdx.z * slab, s_end = min(cols, s_begin + slab);
-  const int m_valid = min(TM, NA - i0), n_valid = min(TN, n_out - j0);
+  const int m_valid = min(TM, n_in - i0), n_valid = min(TN, n_out - j0);
   const int n_tile = (n_valid + 15) & ~15;
+  const bool bias_cta = blockIdx.x == 0 && b_off >= 0;
+  if ((skip_tiles >> (blockIdx.x * gridDim.y + blockIdx.y)) & 1ull) {  // every weight of this tile is masked: exact-zero gradient
+    if (!bias_cta) return;
+    // still owes the bias gradient of its columns: plain column sums, no tensor core
+    for (int j = warp; j < n_valid; j += NTHR / 32) {
+      const float* g = rows + (size_t)(g_row + j0 + j) * C;
+      float a = 0.0f;
+      for (int s = s_begin + lane; s < s_end; s += 32) a += g[s];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) atomicAdd(grad + b_off + j0 + j, a);
+    }
+    return;
+  }
   const uint32_t tmem_d = tmem_alloc(sm, warp);
-  const int ones_r = (b_off >= 0 && n_in - i0 >= 0 && n_in - i0 < TM) ? n_in - i0 : -1;  // tile row of the ones row
-  // row 0 of the workspace is the constant-ones row (vm_ops.cuh ROW_ONES)
-  LoadKMajor la{rows + (size_t)(in_row + i0) * C + s_begin, (size_t)C, TM, m_valid, ones_r, rows + s_begin};
+  LoadKMajor la{rows + (size_t)(in_row + i0) * C + s_begin, (size_t)C, TM, m_valid, -1, nullptr};
   LoadKMajor lb{rows + (size_t)(g_row + j0) * C + s_begin, (size_t)C, n_tile, n_valid, -1, nullptr};
   const int lane_base = 32 * (warp & 3), col0 = NCOL * (warp >> 2);
   float acc[NCOL];
   k_loop(sm, tmem_d, n_tile, s_end - s_begin, lane_base, col0, la, lb, acc);
   const int i = i0 + lane_base + lane;  // TMEM lane = input index
-  if (i < NA) {
-    float* dst = grad + (i < n_in ? w_off + (size_t)i * ld : (size_t)b_off) + j0 + col0;
+  if (i < n_in) {
+    float* dst = grad + w_off + (size_t)i * ld + j0 + col0;
 #pragma unroll
     for (int c = 0; c < NCOL; ++c)
       if (col0 + c < n_valid) atomicAdd(dst + c, acc[c]);
+  }
+  if (bias_cta) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = LoadKMajor::row_of(tid, it);
+      if (r < n_valid) atomicAdd(grad + b_off + j0 + r, lb.rs[it]);
+    }
   }
   tmem_free(tmem_d, warp);
 }
