@@ -6,38 +6,6 @@
 
 namespace surj {
 
-// ---------------------------------------------------------------- value types
-// f2 is a 64-bit register pair worked on by PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2, which also
-// take a broadcast scalar or an immediate as an operand: every product of the conditioner networks for both samples
-// is ONE instruction fed by ONE warp-uniform weight load.  Each lane is a correctly rounded FP32 operation.
-struct f2 {
-  u64 v;
-  f2() = default;
-  SURJ_DEV f2(float s) { asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(s)); }
-  SURJ_DEV f2(float lo, float hi) { asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi)); }
-  SURJ_DEV float lo() const { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
-  SURJ_DEV float hi() const { return __uint_as_float((unsigned)(v >> 32)); }
-};
-SURJ_DEV f2 operator+(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-SURJ_DEV f2 operator-(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-SURJ_DEV f2 operator*(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-SURJ_DEV f2 operator-(f2 a) { return f2(0.0f) - a; }
-SURJ_DEV f2 operator/(f2 a, f2 b) { return f2(a.lo() / b.lo(), a.hi() / b.hi()); }
-SURJ_DEV f2& operator+=(f2& a, f2 b) { a = a + b; return a; }
-using ::fmaf;  // keep the scalar overload visible next to the packed one
-SURJ_DEV f2 fmaf(f2 a, f2 b, f2 c) {
-  f2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
-  return r;
-}
-
-template <class V>
-struct Lanes;
-template <>
-struct Lanes<float> { static constexpr int W = 1; };
-template <>
-struct Lanes<f2> { static constexpr int W = 2; };
-
 // per-lane map of a scalar function (transcendentals, selects: MUFU and FSEL have no packed form)
 template <class F>
 SURJ_DEV float vmap(float a, F f) { return f(a); }
@@ -47,8 +15,6 @@ template <class F>
 SURJ_DEV float vmap(float a, float b, F f) { return f(a, b); }
 template <class F>
 SURJ_DEV f2 vmap(f2 a, f2 b, F f) { return f2(f(a.lo(), b.lo()), f(a.hi(), b.hi())); }
-SURJ_DEV float hsum(float a) { return a; }
-SURJ_DEV float hsum(f2 a) { return a.lo() + a.hi(); }
 
 
 // both lanes of the approximate sigmoid used for hidden activations: 1 / (1 + 2^(-x log2 e)), multiplies packed

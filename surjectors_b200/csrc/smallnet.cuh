@@ -37,6 +37,36 @@ enum : int { LAYOUT_SPLIT = 0, LAYOUT_INTERLEAVED = 1 };
 #define SURJ_DEV __device__ __forceinline__
 #define SURJ_HALF_LOG_2PI 0.91893853320467274178f
 
+// ---------------------------------------------------------------- value types
+// f2 is a 64-bit register pair worked on by PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2, which also
+// take a broadcast scalar or an immediate as an operand; each lane is a correctly rounded FP32 operation and the pair
+// issues at the full FP32 rate in ONE issue slot (tools/ubench/ffma2.cu).  Used two ways: the matvecs below pack two
+// adjacent OUTPUTS of one sample (one broadcast activation x two adjacent weights), and the compact kernel
+// (compact.cuh, packed.cuh) packs two SAMPLES per thread.
+struct f2 {
+  u64 v;
+  f2() = default;
+  SURJ_DEV f2(float s) { asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(s)); }
+  SURJ_DEV f2(float lo, float hi) { asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi)); }
+  SURJ_DEV float lo() const { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+  SURJ_DEV float hi() const { return __uint_as_float((unsigned)(v >> 32)); }
+};
+SURJ_DEV f2 operator+(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SURJ_DEV f2 operator-(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SURJ_DEV f2 operator*(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SURJ_DEV f2 operator-(f2 a) { return f2(0.0f) - a; }
+SURJ_DEV f2 operator/(f2 a, f2 b) { return f2(a.lo() / b.lo(), a.hi() / b.hi()); }
+SURJ_DEV f2& operator+=(f2& a, f2 b) { a = a + b; return a; }
+using ::fmaf;  // keep the scalar overload visible next to the packed one
+SURJ_DEV f2 fmaf(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+
+SURJ_DEV float hsum(float a) { return a; }
+SURJ_DEV float hsum(f2 a) { return a.lo() + a.hi(); }
+
 // ------------------------------------------------------------------ scalar math
 // exp feeds log-dets and Gaussian residuals directly: ex2.approx (2 ulp) with the argument's rounding error folded back
 // in, i.e. expf-grade accuracy in 6 instructions.  The sigmoid of swish / sigmoid activations only shapes hidden units:
@@ -152,41 +182,67 @@ struct Lin {
   }
 };
 
+// The three matvecs issue packed FFMA2 over PAIRS OF ADJACENT OUTPUTS (j, j + 1) of the thread's one sample: the
+// activation is the broadcast operand, the two weights are adjacent in the row-major blob (they arrive as halves of the
+// same LDS.128), the accumulator pair is two adjacent registers whose halves the scalar code before / after reads and
+// writes directly.  The generated kernels are bound by instruction delivery, so halving the FMA
+// instructions at an unchanged number of warps is worth ~20 % of the stream.  Pairs of which only one weight is
+// structurally non-zero (P::on) fall back to a scalar FFMA on that half.
+
 // pre[j] = b[j] + sum_i in[i] W[i][j]    (columns with no active row still get their bias:
 // they are real outputs of the reference network unless the caller never reads them)
-template <class L>
-SURJ_DEV void lin_pre(const float* __restrict__ sp, const float (&in)[L::IN], float (&pre)[L::OUT]) {
+template <class L, bool BIAS>
+SURJ_DEV void lin_mac(const float* __restrict__ sp, const float (&in)[L::IN], float (&pre)[L::OUT]) {
+  constexpr int NPAIR = L::OUT / 2;
+  f2 acc[NPAIR > 0 ? NPAIR : 1];
 #pragma unroll
-  for (int j = 0; j < L::OUT; ++j) pre[j] = (L::BOFF >= 0) ? sp[(L::BOFF >= 0 ? L::BOFF : 0) + j] : 0.0f;
+  for (int p = 0; p < NPAIR; ++p) {
+    if (BIAS) acc[p] = (L::BOFF >= 0) ? f2(sp[(L::BOFF >= 0 ? L::BOFF : 0) + 2 * p], sp[(L::BOFF >= 0 ? L::BOFF : 0) + 2 * p + 1]) : f2(0.0f);
+    else acc[p] = f2(pre[2 * p], pre[2 * p + 1]);
+  }
+  float tail = 0.0f;  // last column of an odd-width layer
+  if (L::OUT & 1) tail = BIAS ? ((L::BOFF >= 0) ? sp[(L::BOFF >= 0 ? L::BOFF : 0) + L::OUT - 1] : 0.0f) : pre[L::OUT - 1];
 #pragma unroll
   for (int i = 0; i < L::IN; ++i) {
 #pragma unroll
-    for (int j = 0; j < L::OUT; ++j)
-      if (L::P::on(i, j)) pre[j] = fmaf(in[i], sp[L::WOFF + i * L::OUT + j], pre[j]);
+    for (int p = 0; p < NPAIR; ++p) {
+      const int o = L::WOFF + i * L::OUT + 2 * p;
+      const bool lo_on = L::P::on(i, 2 * p), hi_on = L::P::on(i, 2 * p + 1);
+      if (lo_on && hi_on) acc[p] = fmaf(f2(in[i]), f2(sp[o], sp[o + 1]), acc[p]);
+      else if (lo_on) acc[p] = f2(fmaf(in[i], sp[o], acc[p].lo()), acc[p].hi());
+      else if (hi_on) acc[p] = f2(acc[p].lo(), fmaf(in[i], sp[o + 1], acc[p].hi()));
+    }
+    if ((L::OUT & 1) && L::P::on(i, L::OUT - 1)) tail = fmaf(in[i], sp[L::WOFF + i * L::OUT + L::OUT - 1], tail);
   }
+#pragma unroll
+  for (int p = 0; p < NPAIR; ++p) { pre[2 * p] = acc[p].lo(); pre[2 * p + 1] = acc[p].hi(); }
+  if (L::OUT & 1) pre[L::OUT - 1] = tail;
 }
-
+template <class L>
+SURJ_DEV void lin_pre(const float* __restrict__ sp, const float (&in)[L::IN], float (&pre)[L::OUT]) { lin_mac<L, true>(sp, in, pre); }
 // accumulate only: pre[j] += sum_i in[i] W[i][j]
 template <class L>
-SURJ_DEV void lin_acc(const float* __restrict__ sp, const float (&in)[L::IN], float (&pre)[L::OUT]) {
-#pragma unroll
-  for (int i = 0; i < L::IN; ++i) {
-#pragma unroll
-    for (int j = 0; j < L::OUT; ++j)
-      if (L::P::on(i, j)) pre[j] = fmaf(in[i], sp[L::WOFF + i * L::OUT + j], pre[j]);
-  }
-}
+SURJ_DEV void lin_acc(const float* __restrict__ sp, const float (&in)[L::IN], float (&pre)[L::OUT]) { lin_mac<L, false>(sp, in, pre); }
 
 // g_in[i] (+)= sum_j W[i][j] g_pre[j]
 template <class L, bool ACCUM>
 SURJ_DEV void lin_bwd_in(const float* __restrict__ sp, const float (&g_pre)[L::OUT], float (&g_in)[L::IN]) {
+  constexpr int NPAIR = L::OUT / 2;
 #pragma unroll
   for (int i = 0; i < L::IN; ++i) {
     float a = ACCUM ? g_in[i] : 0.0f;
+    f2 a2 = f2(0.0f);
+    bool any_pair = false;
 #pragma unroll
-    for (int j = 0; j < L::OUT; ++j)
-      if (L::P::on(i, j)) a = fmaf(sp[L::WOFF + i * L::OUT + j], g_pre[j], a);
-    g_in[i] = a;
+    for (int p = 0; p < NPAIR; ++p) {
+      const int o = L::WOFF + i * L::OUT + 2 * p;
+      const bool lo_on = L::P::on(i, 2 * p), hi_on = L::P::on(i, 2 * p + 1);
+      if (lo_on && hi_on) { a2 = fmaf(f2(sp[o], sp[o + 1]), f2(g_pre[2 * p], g_pre[2 * p + 1]), a2); any_pair = true; }
+      else if (lo_on) a = fmaf(sp[o], g_pre[2 * p], a);
+      else if (hi_on) a = fmaf(sp[o + 1], g_pre[2 * p + 1], a);
+    }
+    if ((L::OUT & 1) && L::P::on(i, L::OUT - 1)) a = fmaf(sp[L::WOFF + i * L::OUT + L::OUT - 1], g_pre[L::OUT - 1], a);
+    g_in[i] = any_pair ? a + hsum(a2) : a;
   }
 }
 
