@@ -83,14 +83,17 @@ Command (B200, `gpurun`): `ncu --set full --clock-control none --import-source o
 Top warp stall reasons (warps stalled per issue-active cycle): {', '.join(f'{n} {v:.2f}' for v, n in st)}.
 
 Reading: DRAM traffic per launch = {rd / 1e6:.2f} MB read + {wr / 1e6:.2f} MB written vs 5.51 MB algorithmic
-(84 B/sample x 65536 + parameters): no re-reads, the kernel is not memory bound.  It is instruction-fetch / latency bound:
-`no_instruction` is the top stall (the straight-line stream is ~160 KB per warp, SM instruction-cache hit rate
-{d['sm__icc_request_hit_rate.pct'][0][:5]} %), 16 resident warps per SM (register-limited at 128), FMA pipe about a fifth active.
+(84 B/sample x 65536 + parameters): no re-reads, the kernel is not memory bound.  It is latency bound on two fronts:
+`short_scoreboard` (the warp-uniform LDS.128 weight loads and the shared-memory contraction feeding dependent FFMA2 /
+FFMA) and `no_instruction` (the straight-line stream is ~140 KB per warp, SM instruction-cache hit rate
+{d['sm__icc_request_hit_rate.pct'][0][:5]} %), at 13.8 resident warps per SM (batch 65 536 = 443 samples per SM; register-limited
+at 128); FMA pipe about a fifth active.
 History of this kernel in round 1 (CUDA-event time of kernel + reduction): 248 us (shared-memory float atomics in the gradient
 contraction) -> 92 us (shuffle-combined, atomics-free contraction) -> 62 us (register cap 128, 64-thread CTAs, 8 CTAs/SM;
 128/256/512-thread CTAs measured 79/118/145 us, 5-6 CTAs/SM 87 us) -> 59 us (one conditioner forward per layer in the backward)
 -> 57 us (ticketed reduction with fused Adam) -> 53 us (approximate sigmoid for hidden activations only) -> 52 us
-(MUFU-only sigmoid, 6-instruction expf-grade exp).  See DESIGN.md section 2 for the instruction-delivery microbenchmarks and
+(MUFU-only sigmoid, 6-instruction expf-grade exp; packing the matvecs into FFMA2 over output pairs then removed another
+8 % of the instructions -- 60.4 vs 64.8 us under ncu -- but under 1 % of the warm, graph-replayed step).  See DESIGN.md section 2 for the instruction-delivery microbenchmarks and
 the two alternative kernels measured against this one.
 """)
   open(os.path.join(P, "r1_launch_lists.md"), "w").write(f"""# ncu launch lists (`--metrics gpu__time_duration.sum --clock-control none`), round 1
