@@ -113,7 +113,7 @@ CcPlan* cc_compile(const SurjPlan* plan, std::string* why) {
     L.t_idx = (int)itab.size(); itab.insert(itab.end(), tdims.begin(), tdims.end());
     L.p_idx = (int)itab.size(); itab.insert(itab.end(), pdims.begin(), pdims.end());
     auto stage_mlp = [&](const SurjMlpDesc& m, int H, const std::vector<int>& in_dims, const std::vector<int>& out_cols, Mlp& M) {
-      const int win = m.widths[0], wout = m.widths[3];
+      const int wout = m.widths[3];
       M.n_in = (int)in_dims.size();
       M.w1 = stage_block(M.n_in * H);
       for (int k = 0; k < M.n_in; ++k)
@@ -131,7 +131,6 @@ CcPlan* cc_compile(const SurjPlan* plan, std::string* why) {
         for (int i = 0; i < H; ++i) src[M.w3t + (int)o * H + i] = (int)m.w_off[2] + i * wout + out_cols[o];
         src[M.b3 + (int)o] = (int)m.b_off[2] + out_cols[o];
       }
-      (void)win;
     };
     // conditioner: inputs = pass-through dims (the masked input is zero elsewhere, masked_coupling.py:75-77);
     // outputs needed = (shift, log_scale) of the transformed dims in bijector_fn's layout
