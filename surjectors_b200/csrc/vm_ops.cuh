@@ -91,20 +91,38 @@ VM_DEV void op_affine(Ctx<NT, S>& c, const Op& op) {
   const int in_row = op.a[0], out_row = op.a[1], n_t = op.a[2], it = op.a[3], sh = op.a[4], ss = op.a[5], ls = op.a[6],
             lss = op.a[7], inner = op.a[8];
   const float lpw = op.a[9] ? 0.0f : 1.0f;
-  for (int k = 0; k < n_t; ++k) {
-    const int d = c.itab[it + k];
+  // U dims at a time, all loads issued before the first use: out of global memory (per-op executor) a thread's rows are
+  // ~1 us away, and one load -> exp -> store chain per dim left the kernel at 1 TB/s (ncu: long_scoreboard 19-42)
+  constexpr int U = 4;
+  for (int k0 = 0; k0 < n_t; k0 += U) {
+    int d[U];
+    float y[U][S], m[U][S], l[U][S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const float y = c.row(in_row + d)[s * NT], m = c.row(sh + k * ss)[s * NT], l = c.row(ls + k * lss)[s * NT];
-      float z;
-      if (inner == INNER_AFFINE) {  // ScalarAffine(m, exp(l)).inverse: z = (y - m) e^{-l}, ld = -l
-        z = (y - m) * expf(-l);
-        c.lp[s] -= lpw * l;
-      } else {  // Inverse(ScalarAffine).inverse = forward: z = e^{l} y + m, ld = +l
-        z = fmaf(expf(l), y, m);
-        c.lp[s] += lpw * l;
+    for (int u = 0; u < U; ++u) {
+      const int k = min(k0 + u, n_t - 1);
+      d[u] = c.itab[it + k];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        y[u][s] = c.row(in_row + d[u])[s * NT];
+        m[u][s] = c.row(sh + k * ss)[s * NT];
+        l[u][s] = c.row(ls + k * lss)[s * NT];
       }
-      c.row(out_row + d)[s * NT] = z;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (k0 + u >= n_t) break;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float z;
+        if (inner == INNER_AFFINE) {  // ScalarAffine(m, exp(l)).inverse: z = (y - m) e^{-l}, ld = -l
+          z = (y[u][s] - m[u][s]) * expf(-l[u][s]);
+          c.lp[s] -= lpw * l[u][s];
+        } else {  // Inverse(ScalarAffine).inverse = forward: z = e^{l} y + m, ld = +l
+          z = fmaf(expf(l[u][s]), y[u][s], m[u][s]);
+          c.lp[s] += lpw * l[u][s];
+        }
+        c.row(out_row + d[u])[s * NT] = z;
+      }
     }
   }
 }
@@ -114,30 +132,46 @@ template <int NT, int S>
 VM_DEV void op_affine_bwd(Ctx<NT, S>& c, const Op& op) {
   const int in_row = op.a[0], n_t = op.a[1], it = op.a[2], sh = op.a[3], ss = op.a[4], ls = op.a[5], lss = op.a[6],
             inner = op.a[7], gout = op.a[8], gin = op.a[9];
-  for (int k = 0; k < n_t; ++k) {
-    const int d = c.itab[it + k];
+  constexpr int U = 4;
+  for (int k0 = 0; k0 < n_t; k0 += U) {
+    int d[U];
+    float y[U][S], m[U][S], l[U][S], gz[U][S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const float y = c.row(in_row + d)[s * NT];
-      float* pm = c.row(sh + k * ss) + s * NT;
-      float* pl = c.row(ls + k * lss) + s * NT;
-      const float m = *pm, l = *pl, gz = c.row(gout + d)[s * NT], glc = c.glp[s];
-      float gy, gm, gs;
-      if (inner == INNER_AFFINE) {
-        const float e = expf(-l);
-        const float z = (y - m) * e;
-        gy = gz * e;
-        gm = -gy;
-        gs = -gz * z - glc;
-      } else {
-        const float e = expf(l);
-        gy = gz * e;
-        gm = gz;
-        gs = gz * e * y + glc;
+    for (int u = 0; u < U; ++u) {
+      const int k = min(k0 + u, n_t - 1);
+      d[u] = c.itab[it + k];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        y[u][s] = c.row(in_row + d[u])[s * NT];
+        m[u][s] = c.row(sh + k * ss)[s * NT];
+        l[u][s] = c.row(ls + k * lss)[s * NT];
+        gz[u][s] = c.row(gout + d[u])[s * NT];
       }
-      *pm = gm;
-      *pl = gs;
-      c.row(gin + d)[s * NT] = gy;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u;
+      if (k >= n_t) break;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const float glc = c.glp[s];
+        float gy, gm, gs;
+        if (inner == INNER_AFFINE) {
+          const float e = expf(-l[u][s]);
+          const float z = (y[u][s] - m[u][s]) * e;
+          gy = gz[u][s] * e;
+          gm = -gy;
+          gs = -gz[u][s] * z - glc;
+        } else {
+          const float e = expf(l[u][s]);
+          gy = gz[u][s] * e;
+          gm = gz[u][s];
+          gs = gz[u][s] * e * y[u][s] + glc;
+        }
+        c.row(sh + k * ss)[s * NT] = gm;
+        c.row(ls + k * lss)[s * NT] = gs;
+        c.row(gin + d[u])[s * NT] = gy;
+      }
     }
   }
 }
@@ -219,11 +253,20 @@ VM_DEV bool exec_simple(Ctx<NT, S>& c, const Op& op, const Io& io, float& lp_tot
     case OP_LOAD: op_load<NT, S>(c, op, op.a[2] == 0 ? io.y : io.x); return true;
     case OP_STORE: op_store<NT, S>(c, op, op.a[2] == 0 ? io.z_out : (op.a[2] == 1 ? io.g_y : io.g_x)); return true;
     case OP_GATHER:
-      for (int k = 0; k < op.a[1]; ++k) {
-        const float* src = c.row(c.itab[op.a[2] + k]);
-        float* dst = c.row(op.a[0] + k);
+      for (int k0 = 0; k0 < op.a[1]; k0 += 8) {  // 8 rows in flight
+        float v[8][S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) dst[s * NT] = src[s * NT];
+        for (int u = 0; u < 8; ++u) {
+          const float* src = c.row(c.itab[op.a[2] + min(k0 + u, op.a[1] - 1)]);
+#pragma unroll
+          for (int s = 0; s < S; ++s) v[u][s] = src[s * NT];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (k0 + u >= op.a[1]) break;
+#pragma unroll
+          for (int s = 0; s < S; ++s) c.row(op.a[0] + k0 + u)[s * NT] = v[u][s];
+        }
       }
       return true;
     case OP_SCATTER_ADD:
@@ -235,14 +278,23 @@ VM_DEV bool exec_simple(Ctx<NT, S>& c, const Op& op, const Io& io, float& lp_tot
       }
       return true;
     case OP_COPY:
-      for (int k = 0; k < op.a[2]; ++k)
-#pragma unroll
-        for (int s = 0; s < S; ++s) c.row(op.a[0] + k)[s * NT] = c.row(op.a[1] + k)[s * NT];
-      return true;
     case OP_ADD:
-      for (int k = 0; k < op.a[2]; ++k)
+      for (int k0 = 0; k0 < op.a[2]; k0 += 8) {  // 8 rows in flight
+        float v[8][S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) c.row(op.a[0] + k)[s * NT] += c.row(op.a[1] + k)[s * NT];
+        for (int u = 0; u < 8; ++u) {
+          const int k = min(k0 + u, op.a[2] - 1);
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            v[u][s] = c.row(op.a[1] + k)[s * NT] + (op.code == OP_ADD ? c.row(op.a[0] + k)[s * NT] : 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (k0 + u >= op.a[2]) break;
+#pragma unroll
+          for (int s = 0; s < S; ++s) c.row(op.a[0] + k0 + u)[s * NT] = v[u][s];
+        }
+      }
       return true;
     case OP_ZERO:
       for (int k = 0; k < op.a[1]; ++k)
@@ -301,12 +353,21 @@ VM_DEV bool exec_simple(Ctx<NT, S>& c, const Op& op, const Io& io, float& lp_tot
     case OP_AFFINE_BWD: op_affine_bwd<NT, S>(c, op); return true;
     case OP_RQS_BWD: op_rqs_bwd<NT, S>(c, op); return true;
     case OP_ACT_BWD:
-      for (int k = 0; k < op.a[2]; ++k)
+      for (int k0 = 0; k0 < op.a[2]; k0 += 4) {  // 4 rows in flight
+        float g[4][S], a[4][S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          float* g = c.row(op.a[0] + k) + s * NT;
-          *g = act_bwd(op.a[3], c.row(op.a[1] + k)[s * NT], *g);
+        for (int u = 0; u < 4; ++u) {
+          const int k = min(k0 + u, op.a[2] - 1);
+#pragma unroll
+          for (int s = 0; s < S; ++s) { g[u][s] = c.row(op.a[0] + k)[s * NT]; a[u][s] = c.row(op.a[1] + k)[s * NT]; }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k0 + u >= op.a[2]) break;
+#pragma unroll
+          for (int s = 0; s < S; ++s) c.row(op.a[0] + k0 + u)[s * NT] = act_bwd(op.a[3], a[u][s], g[u][s]);
+        }
+      }
       return true;
     case OP_SCALAR_BWD: {
       float v = 0.0f;
