@@ -217,6 +217,8 @@ MadeMats build_made(Builder& B, const SurjMadeDesc& d) {
 
 struct LayerCode {
   std::vector<Op> fwd;    // inference-mode forward
+  std::vector<Op> dec;    // funnels: decoder forward + backward, run FIRST in the backward program -- it only needs the layer's
+                          // kept output rows, so its scratch rows are released before the conditioner's are allocated
   std::vector<Op> train;  // training-mode forward recompute (keeps pre-activations)
   std::vector<Op> bwd;    // backward, assumes `train` just ran with the same scratch layout
   std::vector<Op> gen;    // sampling direction: forward_and_likelihood_contribution (E[l+1] -> E[l])
@@ -398,18 +400,19 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
           B.scratch_reset();
           std::vector<NetRows> rows, drows;
           int m_row, c_row = -1;
-          emit_fwd(C.train, true, rows, m_row);
-          const int th = rows.back().post_row;
           if (funnel) {
-            emit_dec_fwd(C.train, true, drows, c_row);
+            emit_dec_fwd(C.dec, true, drows, c_row);
             const int thd = drows.back().post_row;
-            C.bwd.push_back(mk(vm::OP_NORMAL_LP_BWD, {Ein + K, nv, thd, thd + nv, Gin + K}));
-            emit_mlp_bwd(C.bwd, drows, true);
-            C.bwd.push_back(mk(vm::OP_ADD, {Gout, c_row, K}));
-            if (dxu) C.bwd.push_back(mk(vm::OP_ADD, {GX, c_row + K, dxu}));
+            C.dec.push_back(mk(vm::OP_NORMAL_LP_BWD, {Ein + K, nv, thd, thd + nv, Gin + K}));
+            emit_mlp_bwd(C.dec, drows, true);
+            C.dec.push_back(mk(vm::OP_ADD, {Gout, c_row, K}));
+            if (dxu) C.dec.push_back(mk(vm::OP_ADD, {GX, c_row + K, dxu}));
+            B.scratch_reset();  // the decoder is done: the conditioner reuses its rows
           } else {
             C.bwd.push_back(mk(vm::OP_COPY, {Gin, Gout, D}));
           }
+          emit_fwd(C.train, true, rows, m_row);
+          const int th = rows.back().post_row;
           inner_bwd(C.bwd, n_t, t_dims, th, false);
           emit_mlp_bwd(C.bwd, rows, true);
           if (n_pass > 0) {
@@ -497,18 +500,19 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
         {
           B.scratch_reset();
           MadeRows R;
-          emit_fwd(C.train, true, R);
-          const int th = R.rest.back().post_row;
           if (funnel) {
             std::vector<NetRows> drows;
             int c_row;
-            emit_dec_fwd(C.train, true, drows, c_row);
+            emit_dec_fwd(C.dec, true, drows, c_row);
             const int thd = drows.back().post_row;
-            C.bwd.push_back(mk(vm::OP_NORMAL_LP_BWD, {Ein + K, nv, thd, thd + nv, Gin + K}));
-            emit_mlp_bwd(C.bwd, drows, true);
-            C.bwd.push_back(mk(vm::OP_ADD, {Gout, c_row, K}));
-            if (dxu) C.bwd.push_back(mk(vm::OP_ADD, {GX, c_row + K, dxu}));
+            C.dec.push_back(mk(vm::OP_NORMAL_LP_BWD, {Ein + K, nv, thd, thd + nv, Gin + K}));
+            emit_mlp_bwd(C.dec, drows, true);
+            C.dec.push_back(mk(vm::OP_ADD, {Gout, c_row, K}));
+            if (dxu) C.dec.push_back(mk(vm::OP_ADD, {GX, c_row + K, dxu}));
+            B.scratch_reset();  // the decoder is done: the MADE reuses its rows
           }
+          emit_fwd(C.train, true, R);
+          const int th = R.rest.back().post_row;
           inner_bwd(C.bwd, Dm, t_dims, th, true);
           emit_mlp_bwd(C.bwd, R.rest, true);  // cotangent of h0 lands in the h0 rows
           if (act != vm::ACT_IDENTITY) C.bwd.push_back(mk(vm::OP_ACT_BWD, {R.h0_row, R.p0_row, mm.l0.n_out, act}));
@@ -686,6 +690,7 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
   v->ops_bwd.push_back(mk(vm::OP_BASE_BWD, {E[L], dz, G[0]}));
   if (dx > 0) v->ops_bwd.push_back(mk(vm::OP_ZERO, {GX, dx}));
   for (int l = L - 1; l >= 0; --l) {
+    v->ops_bwd.insert(v->ops_bwd.end(), code[l].dec.begin(), code[l].dec.end());
     v->ops_bwd.insert(v->ops_bwd.end(), code[l].train.begin(), code[l].train.end());
     v->ops_bwd.insert(v->ops_bwd.end(), code[l].bwd.begin(), code[l].bwd.end());
   }
