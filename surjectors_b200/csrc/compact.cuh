@@ -1,14 +1,17 @@
 // Compact fused kernel for chains of affine MaskedCoupling / MaskedCouplingInferenceFunnel layers with small
 // two-hidden-layer MLP conditioners (BASELINE cfg2 and its family), sm_100a.
 //
-// Why a third fused kernel.  The generated straight-line kernels (chain.cuh) are bound by instruction FETCH, not
-// by any pipe: 10k instructions executed once per warp.  tools/ubench/icache.cu measured the law on a B200: code
-// that does not loop inside ~32 KB is issued at <= 0.16 instructions/clk per warp and <= 2.3 per SM however many
-// warps are resident (3.55 per SM for a 24-32 KB loop).  So this kernel is LOOPS: one body per layer kind, driven
-// by a small layer table, about 2k instructions in total.
+// Why a third fused kernel.  The generated straight-line kernels (chain.cuh) execute ~10k instructions once per
+// warp, and tools/ubench/icache.cu measured what that costs on a B200: code that does not loop inside ~32 KB is
+// issued at <= 0.16 instructions/clk per warp and <= 2.3 per SM however many warps are resident (3.55 per SM for a
+// 24-32 KB loop).  So this kernel is LOOPS: one body per layer kind, driven by a small layer table, about 3k
+// instructions in total (instruction-cache hit rate 98 %), and it needs no build-time code generation.  What it
+// pays for that is shared memory: ~106 rows x 448 samples leave room for one 224-thread CTA (7 warps) per SM, and
+// at that occupancy it runs the cfg2 train step in 67 us against 52 us for the generated kernel (DESIGN.md
+// section 2), so AUTO uses it for chains of its family that have no generated kernel.
 //
 //   * a CTA owns a tile of T = 2 * NT samples; every thread owns TWO consecutive samples as packed f32x2 pairs
-//     (FFMA2 / FADD2 / FMUL2, smallnet.cuh) -- one warp-uniform LDS.128 of weights feeds four FFMA2 = 8 FMAs;
+//     (FFMA2 / FADD2 / FMUL2, smallnet.cuh / packed.cuh) -- one warp-uniform LDS.128 of weights feeds four FFMA2 = 8 FMAs;
 //   * wide per-sample vectors (layer inputs, conditioner / decoder outputs, cotangents) live in shared memory as
 //     rows [feature][sample] (a thread only touches its own 8-byte column: conflict-free, no barrier);
 //   * the NARROW hidden layers (width H <= 16, a template constant) live in registers, so the three matvecs of a
