@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128)
 vg_elem(const Op* __restrict__ ops, int n_ops, int first, Io io, float* __restrict__ rows, int C, long long base,
         long long B, const int32_t* __restrict__ itab, const float* __restrict__ scal, float* __restrict__ scal_g,
         float* __restrict__ loss_acc) {
-  Ctx<128, 1> c;
+  Ctx<128, 1, true> c;
   c.rows = rows; c.T = C; c.col = blockIdx.x * 128 + threadIdx.x; c.base = base; c.B = B;
   c.itab = itab; c.scal = scal; c.scal_g = scal_g;
   const long long g = c.sample(0);
@@ -64,7 +64,7 @@ vg_elem(const Op* __restrict__ ops, int n_ops, int first, Io io, float* __restri
   bool stored = false;
   for (int pc = 0; pc < n_ops; ++pc) {
     const Op op = ops[pc];
-    exec_simple<128, 1>(c, op, io, lp_total);
+    exec_simple<128, 1, true>(c, op, io, lp_total);
     stored |= op.code == OP_STORE_LP;
   }
   c.row(ROW_LP)[0] = c.lp[0];

@@ -5,8 +5,8 @@
 namespace vm {
 
 // out[j] = act(init + b[j] + sum_i in[i] W[i][j]) for a chunk of CH outputs at a time.
-template <int NT, int S, int CH>
-VM_DEV void linear_chunks(Ctx<NT, S>& c, const float* __restrict__ par, const Op& op) {
+template <int NT, int S, bool FAR, int CH>
+VM_DEV void linear_chunks(Ctx<NT, S, FAR>& c, const float* __restrict__ par, const Op& op) {
   constexpr int T = NT * S;
   const int in_row = op.a[0], n_in = op.a[1], w_off = op.a[2], ld = op.a[3], out_row = op.a[4], n_out = op.a[5],
             b_off = op.a[6], act = op.a[7], accumulate = op.a[8], pre_row = op.a[9];
@@ -56,18 +56,18 @@ VM_DEV void linear_chunks(Ctx<NT, S>& c, const float* __restrict__ par, const Op
   }
 }
 
-template <int NT, int S>
-VM_DEV void op_linear(Ctx<NT, S>& c, const float* __restrict__ par, const Op& op) {
-  if ((op.a[5] & 15) == 0 && S <= 2) linear_chunks<NT, S, 16>(c, par, op);
-  else linear_chunks<NT, S, 8>(c, par, op);
+template <int NT, int S, bool FAR>
+VM_DEV void op_linear(Ctx<NT, S, FAR>& c, const float* __restrict__ par, const Op& op) {
+  if ((op.a[5] & 15) == 0 && S <= 2) linear_chunks<NT, S, FAR, 16>(c, par, op);
+  else linear_chunks<NT, S, FAR, 8>(c, par, op);
 }
 
 // Weight gradient: grad[W] += in^T g, grad[b] += sum g, contracted over the T samples of the tile by
 // the whole CTA.  Work item = a 4x4 tile of (input, output) pairs x one of KS slices of the sample
 // axis; the KS lanes of one tile are adjacent, combine with shuffles, and the first of them is the
 // only thread of the CTA that ever updates those accumulator addresses (no atomics, deterministic).
-template <int NT, int S>
-VM_DEV void op_linear_dw(Ctx<NT, S>& c, float* __restrict__ grad, const Op& op) {
+template <int NT, int S, bool FAR>
+VM_DEV void op_linear_dw(Ctx<NT, S, FAR>& c, float* __restrict__ grad, const Op& op) {
   constexpr int T = NT * S;
   const int in_row = op.a[0], n_in = op.a[1], g_row = op.a[2], n_out = op.a[3], w_off = op.a[4], ld = op.a[5],
             b_off = op.a[6];
@@ -189,9 +189,9 @@ vm_kernel(Program P, Io io, const float* __restrict__ params, float* __restrict_
     }
     for (int pc = 0; pc < n_ops; ++pc) {
       const Op& op = sops[pc];
-      if (op.code == OP_LINEAR) op_linear<NT, S>(c, par, op);
-      else if (op.code == OP_LINEAR_DW) op_linear_dw<NT, S>(c, grad, op);
-      else exec_simple<NT, S>(c, op, io, lp_total);
+      if (op.code == OP_LINEAR) op_linear<NT, S, false>(c, par, op);
+      else if (op.code == OP_LINEAR_DW) op_linear_dw<NT, S, false>(c, grad, op);
+      else exec_simple<NT, S, false>(c, op, io, lp_total);
     }
   }
   if (!backward) return;

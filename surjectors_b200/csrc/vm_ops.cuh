@@ -17,8 +17,11 @@ struct Io {  // caller buffers of one C-ABI call
   float g_scale; int with_base; int backward;
 };
 
-template <int NT, int S>
+// FAR: the rows live in global memory (per-op executor) -- per-sample op loops then issue a block of row loads before
+// the first use; in shared memory (fused interpreter) the plain one-row-at-a-time loops are cheaper in registers.
+template <int NT, int S, bool FAR = false>
 struct Ctx {
+  static constexpr bool kFar = FAR;
   float* rows;          // [n_rows][T]
   int T;                // row stride in floats
   int col;              // first column of this thread
@@ -40,8 +43,8 @@ struct ThRow {  // theta accessor: rows th0 + k, this thread's column
   VM_DEV float& operator()(int k) const { return p[(size_t)k * T]; }
 };
 
-template <int NT, int S>
-VM_DEV void op_load(Ctx<NT, S>& c, const Op& op, const float* __restrict__ src) {
+template <int NT, int S, bool FAR>
+VM_DEV void op_load(Ctx<NT, S, FAR>& c, const Op& op, const float* __restrict__ src) {
   const int dst = op.a[0], n = op.a[1];
 #pragma unroll
   for (int s = 0; s < S; ++s) {
@@ -66,8 +69,8 @@ VM_DEV void op_load(Ctx<NT, S>& c, const Op& op, const float* __restrict__ src) 
   }
 }
 
-template <int NT, int S>
-VM_DEV void op_store(Ctx<NT, S>& c, const Op& op, float* __restrict__ dst) {
+template <int NT, int S, bool FAR>
+VM_DEV void op_store(Ctx<NT, S, FAR>& c, const Op& op, float* __restrict__ dst) {
   if (dst == nullptr) return;
   const int src = op.a[0], n = op.a[1];
 #pragma unroll
@@ -86,14 +89,14 @@ VM_DEV void op_store(Ctx<NT, S>& c, const Op& op, float* __restrict__ dst) {
   }
 }
 
-template <int NT, int S>
-VM_DEV void op_affine(Ctx<NT, S>& c, const Op& op) {
+template <int NT, int S, bool FAR>
+VM_DEV void op_affine(Ctx<NT, S, FAR>& c, const Op& op) {
   const int in_row = op.a[0], out_row = op.a[1], n_t = op.a[2], it = op.a[3], sh = op.a[4], ss = op.a[5], ls = op.a[6],
             lss = op.a[7], inner = op.a[8];
   const float lpw = op.a[9] ? 0.0f : 1.0f;
   // U dims at a time, all loads issued before the first use: out of global memory (per-op executor) a thread's rows are
   // ~1 us away, and one load -> exp -> store chain per dim left the kernel at 1 TB/s (ncu: long_scoreboard 19-42)
-  constexpr int U = 4;
+  constexpr int U = FAR ? 4 : 1;
   for (int k0 = 0; k0 < n_t; k0 += U) {
     int d[U];
     float y[U][S], m[U][S], l[U][S];
@@ -128,11 +131,11 @@ VM_DEV void op_affine(Ctx<NT, S>& c, const Op& op) {
 }
 
 // cotangents; thetas are overwritten by their cotangents
-template <int NT, int S>
-VM_DEV void op_affine_bwd(Ctx<NT, S>& c, const Op& op) {
+template <int NT, int S, bool FAR>
+VM_DEV void op_affine_bwd(Ctx<NT, S, FAR>& c, const Op& op) {
   const int in_row = op.a[0], n_t = op.a[1], it = op.a[2], sh = op.a[3], ss = op.a[4], ls = op.a[5], lss = op.a[6],
             inner = op.a[7], gout = op.a[8], gin = op.a[9];
-  constexpr int U = 4;
+  constexpr int U = FAR ? 4 : 1;
   for (int k0 = 0; k0 < n_t; k0 += U) {
     int d[U];
     float y[U][S], m[U][S], l[U][S], gz[U][S];
@@ -176,8 +179,8 @@ VM_DEV void op_affine_bwd(Ctx<NT, S>& c, const Op& op) {
   }
 }
 
-template <int NT, int S>
-VM_DEV void op_rqs(Ctx<NT, S>& c, const Op& op) {
+template <int NT, int S, bool FAR>
+VM_DEV void op_rqs(Ctx<NT, S, FAR>& c, const Op& op) {
   const int in_row = op.a[0], out_row = op.a[1], n_t = op.a[2], it = op.a[3], th = op.a[4], K = op.a[5];
   const bool forward = op.a[6] == INNER_RQS_INV;
   const int P = 3 * K + 1;
@@ -197,8 +200,8 @@ VM_DEV void op_rqs(Ctx<NT, S>& c, const Op& op) {
   }
 }
 
-template <int NT, int S>
-VM_DEV void op_rqs_bwd(Ctx<NT, S>& c, const Op& op) {
+template <int NT, int S, bool FAR>
+VM_DEV void op_rqs_bwd(Ctx<NT, S, FAR>& c, const Op& op) {
   const int in_row = op.a[0], n_t = op.a[1], it = op.a[2], th = op.a[3], K = op.a[4];
   const bool forward = op.a[5] == INNER_RQS_INV;
   const int gout = op.a[6], gin = op.a[7];
@@ -214,8 +217,8 @@ VM_DEV void op_rqs_bwd(Ctx<NT, S>& c, const Op& op) {
   }
 }
 
-template <int NT, int S>
-VM_DEV void op_normal_lp(Ctx<NT, S>& c, const Op& op) {
+template <int NT, int S, bool FAR>
+VM_DEV void op_normal_lp(Ctx<NT, S, FAR>& c, const Op& op) {
   const int v = op.a[0], n = op.a[1], mu = op.a[2], ls = op.a[3];
   for (int j = 0; j < n; ++j) {
 #pragma unroll
@@ -227,8 +230,8 @@ VM_DEV void op_normal_lp(Ctx<NT, S>& c, const Op& op) {
   }
 }
 
-template <int NT, int S>
-VM_DEV void op_normal_lp_bwd(Ctx<NT, S>& c, const Op& op) {
+template <int NT, int S, bool FAR>
+VM_DEV void op_normal_lp_bwd(Ctx<NT, S, FAR>& c, const Op& op) {
   const int v = op.a[0], n = op.a[1], mu = op.a[2], ls = op.a[3], gv = op.a[4];
   for (int j = 0; j < n; ++j) {
 #pragma unroll
@@ -247,22 +250,23 @@ VM_DEV void op_normal_lp_bwd(Ctx<NT, S>& c, const Op& op) {
 
 // Executes one simple op; returns false if `op` is a matrix op the caller must handle.
 // lp_total accumulates the log-probs of valid samples stored by OP_STORE_LP (for the loss).
-template <int NT, int S>
-VM_DEV bool exec_simple(Ctx<NT, S>& c, const Op& op, const Io& io, float& lp_total) {
+template <int NT, int S, bool FAR>
+VM_DEV bool exec_simple(Ctx<NT, S, FAR>& c, const Op& op, const Io& io, float& lp_total) {
+  constexpr int UR = FAR ? 8 : 1, UA = FAR ? 4 : 1;  // rows of loads in flight in the copy-like / activation loops
   switch (op.code) {
-    case OP_LOAD: op_load<NT, S>(c, op, op.a[2] == 0 ? io.y : io.x); return true;
-    case OP_STORE: op_store<NT, S>(c, op, op.a[2] == 0 ? io.z_out : (op.a[2] == 1 ? io.g_y : io.g_x)); return true;
+    case OP_LOAD: op_load<NT, S, FAR>(c, op, op.a[2] == 0 ? io.y : io.x); return true;
+    case OP_STORE: op_store<NT, S, FAR>(c, op, op.a[2] == 0 ? io.z_out : (op.a[2] == 1 ? io.g_y : io.g_x)); return true;
     case OP_GATHER:
-      for (int k0 = 0; k0 < op.a[1]; k0 += 8) {  // 8 rows in flight
-        float v[8][S];
+      for (int k0 = 0; k0 < op.a[1]; k0 += UR) {  // UR rows in flight
+        float v[UR][S];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < UR; ++u) {
           const float* src = c.row(c.itab[op.a[2] + min(k0 + u, op.a[1] - 1)]);
 #pragma unroll
           for (int s = 0; s < S; ++s) v[u][s] = src[s * NT];
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < UR; ++u) {
           if (k0 + u >= op.a[1]) break;
 #pragma unroll
           for (int s = 0; s < S; ++s) c.row(op.a[0] + k0 + u)[s * NT] = v[u][s];
@@ -279,17 +283,17 @@ VM_DEV bool exec_simple(Ctx<NT, S>& c, const Op& op, const Io& io, float& lp_tot
       return true;
     case OP_COPY:
     case OP_ADD:
-      for (int k0 = 0; k0 < op.a[2]; k0 += 8) {  // 8 rows in flight
-        float v[8][S];
+      for (int k0 = 0; k0 < op.a[2]; k0 += UR) {  // UR rows in flight
+        float v[UR][S];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < UR; ++u) {
           const int k = min(k0 + u, op.a[2] - 1);
 #pragma unroll
           for (int s = 0; s < S; ++s)
             v[u][s] = c.row(op.a[1] + k)[s * NT] + (op.code == OP_ADD ? c.row(op.a[0] + k)[s * NT] : 0.0f);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < UR; ++u) {
           if (k0 + u >= op.a[2]) break;
 #pragma unroll
           for (int s = 0; s < S; ++s) c.row(op.a[0] + k0 + u)[s * NT] = v[u][s];
@@ -301,9 +305,9 @@ VM_DEV bool exec_simple(Ctx<NT, S>& c, const Op& op, const Io& io, float& lp_tot
 #pragma unroll
         for (int s = 0; s < S; ++s) c.row(op.a[0] + k)[s * NT] = 0.0f;
       return true;
-    case OP_AFFINE: op_affine<NT, S>(c, op); return true;
-    case OP_RQS: op_rqs<NT, S>(c, op); return true;
-    case OP_NORMAL_LP: op_normal_lp<NT, S>(c, op); return true;
+    case OP_AFFINE: op_affine<NT, S, FAR>(c, op); return true;
+    case OP_RQS: op_rqs<NT, S, FAR>(c, op); return true;
+    case OP_NORMAL_LP: op_normal_lp<NT, S, FAR>(c, op); return true;
     case OP_NORMAL_SAMPLE:
       for (int j = 0; j < op.a[1]; ++j)
 #pragma unroll
@@ -349,20 +353,20 @@ VM_DEV bool exec_simple(Ctx<NT, S>& c, const Op& op, const Io& io, float& lp_tot
           c.row(op.a[2] + k)[s * NT] = v;
         }
       return true;
-    case OP_NORMAL_LP_BWD: op_normal_lp_bwd<NT, S>(c, op); return true;
-    case OP_AFFINE_BWD: op_affine_bwd<NT, S>(c, op); return true;
-    case OP_RQS_BWD: op_rqs_bwd<NT, S>(c, op); return true;
+    case OP_NORMAL_LP_BWD: op_normal_lp_bwd<NT, S, FAR>(c, op); return true;
+    case OP_AFFINE_BWD: op_affine_bwd<NT, S, FAR>(c, op); return true;
+    case OP_RQS_BWD: op_rqs_bwd<NT, S, FAR>(c, op); return true;
     case OP_ACT_BWD:
-      for (int k0 = 0; k0 < op.a[2]; k0 += 4) {  // 4 rows in flight
-        float g[4][S], a[4][S];
+      for (int k0 = 0; k0 < op.a[2]; k0 += UA) {  // UA rows in flight
+        float g[UA][S], a[UA][S];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UA; ++u) {
           const int k = min(k0 + u, op.a[2] - 1);
 #pragma unroll
           for (int s = 0; s < S; ++s) { g[u][s] = c.row(op.a[0] + k)[s * NT]; a[u][s] = c.row(op.a[1] + k)[s * NT]; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UA; ++u) {
           if (k0 + u >= op.a[2]) break;
 #pragma unroll
           for (int s = 0; s < S; ++s) c.row(op.a[0] + k0 + u)[s * NT] = act_bwd(op.a[3], a[u][s], g[u][s]);
