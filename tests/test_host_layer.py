@@ -216,3 +216,18 @@ def test_build_fused_kernel_for_a_user_chain(tmp_path):
   assert _runtime.Plan(traced[0]).executor == "fused"
   fused_chains.build_fused_kernel(m, batch, cache_dir=str(tmp_path))
   assert _runtime.Plan(traced[0]).executor == "gen1"
+
+
+def test_forced_executors_refuse_chains_they_do_not_cover():
+  """Forcing an executor never falls back: the compact kernel's family is affine coupling / coupling-funnel chains with
+  two-equal-hidden-layer MLPs, the generated kernels exist only for the compiled-in chains (plan creation is host-only)."""
+  for name, mode, ok in (("cfg2", "compact", True), ("cpl", "compact", True), ("cfg3", "compact", False),
+                         ("cfg4", "compact", False), ("cond", "compact", False), ("cpl", "gen1", False),
+                         ("cfg2", "gen1", True)):
+    c = configs.CONFIGS[name]
+    spec = fused_chains.spec_of(c["make"](), c["dim"], c["dim_x"])
+    if ok:
+      assert _runtime.Plan(spec, mode=_runtime.MODES[mode]).executor == mode, (name, mode)
+    else:
+      with pytest.raises(NotImplementedError):  # SURJ_E_UNSUPPORTED, as the reference raises for unsupported structure
+        _runtime.Plan(spec, mode=_runtime.MODES[mode])
