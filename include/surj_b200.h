@@ -196,13 +196,19 @@ int surj_train_step(const SurjPlan* plan, SurjStream stream, const float* y, con
  * surj_dp_create allocates this rank's mailbox and returns its CUDA IPC handle; the handles of all ranks (in rank
  * order, exchanged by the host, e.g. torch.distributed.all_gather) go to surj_dp_connect; surj_train_step_dp is
  * surj_train_step on the local shard with the sum over ranks inside (2 launches, no NCCL call).  Every rank must
- * call it the same number of times.  surj_dp_error() != 0 reports a peer that did not arrive within ~2 s. */
+ * call it the same number of times.  A peer that does not arrive within the timeout (default 30 s,
+ * SURJ_B200_DP_TIMEOUT_MS or surj_dp_set_timeout_ms; 0 = wait for ever, as a NCCL collective would) sets a sticky
+ * error: the step that timed out and every later one leave params / mu / nu / count untouched (no stale value is
+ * ever summed in), surj_dp_error() (synchronising) and surj_dp_error_nosync() (a host-mapped flag, cheap enough to
+ * poll before every step) return 1, and the caller must stop. */
 #define SURJ_IPC_HANDLE_BYTES 64
 typedef struct SurjDp SurjDp;
 int surj_dp_create(int32_t rank, int32_t world, int64_t n_params, SurjDp** out, unsigned char* handle_out);
 int surj_dp_connect(SurjDp* dp, const unsigned char* handles);
 void surj_dp_destroy(SurjDp* dp);
 int32_t surj_dp_error(const SurjDp* dp);
+int32_t surj_dp_error_nosync(const SurjDp* dp);
+int surj_dp_set_timeout_ms(SurjDp* dp, int64_t ms);
 int surj_train_step_dp(const SurjPlan* plan, SurjDp* dp, SurjStream stream, const float* y, const float* x, float* params,
                        float g_scale, float* g_params, float* mu, float* nu, int32_t* count, float lr, float b1,
                        float b2, float eps, float* loss_out, void* workspace, size_t workspace_bytes, int64_t batch);
@@ -218,6 +224,23 @@ int surj_permutation_inverse(const int32_t* permutation, int32_t n, int32_t* inv
  * launched over every SM; *flops_out = floating-point operations one launch executes.  Gives the
  * measured FP32-pipe peak the small-network kernels are compared against. */
 int surj_bench_fp32_peak(SurjStream stream, int32_t iters, float* sink, double* flops_out);
+/* the same for the tensor pipe: one CTA per SM issues iters x 4 tcgen05.mma.kind::tf32 of 128 x 256 x 8 (A in tensor
+ * memory, B in shared memory); *flops_out = dense TF32 FLOPs of one launch.  The wide-network kernels compute FP32-grade
+ * products as 3 TF32 MMAs, so their roofline peak is this rate / 3. */
+int surj_bench_tf32_peak(SurjStream stream, int32_t iters, float* sink, double* flops_out);
+
+/* --- per-kernel timing of the per-op executor (bench.py's roofline leg; NOT for CUDA-graph capture): between
+ * surj_profile_begin() and surj_profile_end() every launch of the per-op executor is bracketed by CUDA events on its
+ * stream.  surj_profile_end synchronises, writes a JSON object {"kernel kind": {"launches", "ms", "flops"}, ...} into
+ * out (flops = needed FLOPs: structurally non-zero multiply-adds x 2) and returns the number of bytes written
+ * (0: buffer too small / profiling was not on). */
+int surj_profile_begin(void);
+int64_t surj_profile_end(char* out, int64_t out_bytes);
+
+/* --- tuning / test knob of the per-op executor: the number of samples whose rows are resident in the workspace at a
+ * time (rounded up to 128; default 131072, SURJ_B200_CHUNK at load time; 0 restores the default).  Returns the
+ * previous value.  Changes surj_plan_workspace_bytes: query it again after setting. */
+int64_t surj_set_chunk_samples(int64_t samples);
 
 const char* surj_last_error(void);
 int32_t surj_abi_version(void);

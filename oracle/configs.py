@@ -223,7 +223,7 @@ def make_cpl(dim=12, hidden=(16, 16), dec_hidden=(8, 8), activation="tanh"):
   return flow
 
 
-def randomize(params, seed, w_std=0.3, b_val=None, b_std=0.1):
+def randomize(params, seed, w_std=0.3, b_val=None, b_std=0.1, literal=False):
   """Replace haiku-default inits by non-trivial values so every transform is exercised
   (mirrors masked_coupling_test.py:78-82: TruncatedNormal(1.0) weights, ones bias)."""
   rng = np.random.Generator(np.random.PCG64(seed))
@@ -233,7 +233,10 @@ def randomize(params, seed, w_std=0.3, b_val=None, b_std=0.1):
     for name, val in bucket.items():
       if name == "w":
         fan_in = val.shape[0]
-        new = rng.standard_normal(val.shape) * (w_std / np.sqrt(max(fan_in, 1)) * np.sqrt(8.0))
+        if literal:  # per-weight sigma = w_std, truncated at 2 sigma: hk.initializers.TruncatedNormal(stddev=w_std)
+          new = np.clip(rng.standard_normal(val.shape), -2.0, 2.0) * w_std
+        else:
+          new = rng.standard_normal(val.shape) * (w_std / np.sqrt(max(fan_in, 1)) * np.sqrt(8.0))
       elif name == "b":
         new = rng.standard_normal(val.shape) * b_std if b_val is None else np.full(val.shape, b_val)
       elif name in ("lower_entries", "upper_entries"):

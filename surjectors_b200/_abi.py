@@ -112,12 +112,18 @@ _SIGNATURES = {
   "surj_dp_connect": (C.c_int, [C.c_void_p, C.c_char_p]),
   "surj_dp_destroy": (None, [C.c_void_p]),
   "surj_dp_error": (C.c_int32, [C.c_void_p]),
+  "surj_dp_error_nosync": (C.c_int32, [C.c_void_p]),
+  "surj_dp_set_timeout_ms": (C.c_int, [C.c_void_p, C.c_int64]),
   "surj_train_step_dp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                    C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
   "surj_made_masks": (C.c_int64, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8)]),
   "surj_permutation_inverse": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
   "surj_bench_fp32_peak": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]),
+  "surj_bench_tf32_peak": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]),
+  "surj_profile_begin": (C.c_int, []),
+  "surj_profile_end": (C.c_int64, [C.c_char_p, C.c_int64]),
+  "surj_set_chunk_samples": (C.c_int64, [C.c_int64]),
   "surj_last_error": (C.c_char_p, []),
   "surj_abi_version": (C.c_int32, []),
   "surj_registry_size": (C.c_int32, []),

@@ -484,6 +484,8 @@ class TransformedDistribution:
     g = torch.Generator(device="cpu").manual_seed(int(rng.integers(0, 2**62)))
     z = torch.randn((n, d), generator=g, dtype=torch.float32).to(device)
     lp_z = (-0.5 * z * z - 0.9189385332046727).sum(-1)
-    honour_x = not isinstance(self.transform, MaskedCoupling)  # quirk Q1 applies to both directions
-    y, fldj = _runtime.run_forward(self.transform, z, x, honour_x=honour_x)
+    # quirk Q1 is one-sided upstream: inverse_and_log_prob drops x for distrax.Bijector transforms (:87-88), but the
+    # sampling direction always calls transform.forward_and_likelihood_contribution(z, x=x) (:137), so a bare
+    # MaskedCoupling does condition on x when sampling
+    y, fldj = _runtime.run_forward(self.transform, z, x, honour_x=True)
     return y, lp_z - fldj

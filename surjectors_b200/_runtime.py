@@ -47,8 +47,29 @@ class execution_mode:
     _default_mode = self._prev
 
 
+def _on(t):
+  """Make the device of `t` current for the duration of an ABI call: the C side launches on, allocates plan tables
+  on and checks against the CURRENT device (a plan is bound to the device of its first launch)."""
+  return torch.cuda.device(t.device)
+
+
+class chunk_samples:
+  """Context manager: samples per chunk of the per-op executor (tests run multi-chunk cases at small batches)."""
+
+  def __init__(self, samples):
+    self.samples = int(samples)
+
+  def __enter__(self):
+    self._prev = int(_abi.lib().surj_set_chunk_samples(self.samples))
+    return self
+
+  def __exit__(self, *a):
+    _abi.lib().surj_set_chunk_samples(self._prev)
+
+
 class Plan:
-  """Owns a `SurjPlan*`: the compiled description of one chain (what jax.jit's trace cache holds)."""
+  """Owns a `SurjPlan*`: the compiled description of one chain (what jax.jit's trace cache holds).  One Plan per
+  (chain, device): the C object keeps device-resident tables."""
 
   def __init__(self, spec: ChainSpec, base=BASE_STANDARD_NORMAL, mode=_abi.MODE_AUTO):
     lib = _abi.lib()
@@ -99,9 +120,10 @@ class Plan:
       z = torch.empty((B, self.dim_out), dtype=torch.float32, device=y.device)
     if B == 0:
       return z, lp
-    ws, n = self.workspace(B, False, y.device)
-    st = self._lib.surj_chain_logprob_fwd(
-      self._h, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), _ptr(z), lp.data_ptr(), ws.data_ptr(), n, B)
+    with _on(y):
+      ws, n = self.workspace(B, False, y.device)
+      st = self._lib.surj_chain_logprob_fwd(
+        self._h, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), _ptr(z), lp.data_ptr(), ws.data_ptr(), n, B)
     _abi.check(st, "surj_chain_logprob_fwd")
     return z, lp
 
@@ -117,10 +139,11 @@ class Plan:
     if B == 0:
       gp.zero_()
       return gp, gy, gx, lp
-    ws, n = self.workspace(B, True, dev)
-    st = self._lib.surj_chain_logprob_bwd(
-      self._h, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), _ptr(g_lp), float(g_scale), _ptr(g_z),
-      gp.data_ptr(), _ptr(loss_out), _ptr(lp), _ptr(gy), _ptr(gx), ws.data_ptr(), n, B)
+    with _on(y):
+      ws, n = self.workspace(B, True, dev)
+      st = self._lib.surj_chain_logprob_bwd(
+        self._h, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), _ptr(g_lp), float(g_scale), _ptr(g_z),
+        gp.data_ptr(), _ptr(loss_out), _ptr(lp), _ptr(gy), _ptr(gx), ws.data_ptr(), n, B)
     _abi.check(st, "surj_chain_logprob_bwd")
     return gp, gy, gx, lp
 
@@ -137,7 +160,8 @@ def _plan_forward(self, z, x, flat, eps=None):
   ld = torch.empty(B, dtype=torch.float32, device=z.device)
   if B == 0:
     return y, ld
-  n = int(self._lib.surj_plan_forward_workspace_bytes(self._h, B))
+  with _on(z):
+    n = int(self._lib.surj_plan_forward_workspace_bytes(self._h, B))
   key = ("gen", B, str(z.device))
   ws = self._ws.get(key)
   if ws is None or ws.numel() < n:
@@ -147,8 +171,9 @@ def _plan_forward(self, z, x, flat, eps=None):
   if n_eps > 0 and (eps is None or tuple(eps.shape) != (B, n_eps) or eps.dtype != torch.float32 or not eps.is_contiguous()
                     or eps.device != z.device):
     raise ValueError(f"eps must be a contiguous float32 [B, {n_eps}] tensor on the device of z")
-  st = self._lib.surj_chain_forward(self._h, _stream(z), z.data_ptr(), _ptr(x), _ptr(eps) if n_eps else None,
-                                    flat.data_ptr(), y.data_ptr(), ld.data_ptr(), ws.data_ptr(), n, B)
+  with _on(z):
+    st = self._lib.surj_chain_forward(self._h, _stream(z), z.data_ptr(), _ptr(x), _ptr(eps) if n_eps else None,
+                                      flat.data_ptr(), y.data_ptr(), ld.data_ptr(), ws.data_ptr(), n, B)
   _abi.check(st, "surj_chain_forward")
   return y, ld
 
@@ -161,10 +186,11 @@ def _plan_train_step(self, y, x, flat, g_scale, grads, opt, loss_out):
   """surj_train_step: fused log_prob+VJP kernel, gradient reduction with the Adam update in its last stage."""
   B = y.shape[0]
   _check_inputs(self, y, x, flat)
-  ws, n = self.workspace(B, True, y.device)
-  st = self._lib.surj_train_step(
-    self._h, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), float(g_scale), grads.data_ptr(), opt.mu.data_ptr(),
-    opt.nu.data_ptr(), opt.count.data_ptr(), opt.lr, opt.b1, opt.b2, opt.eps, _ptr(loss_out), ws.data_ptr(), n, B)
+  with _on(y):
+    ws, n = self.workspace(B, True, y.device)
+    st = self._lib.surj_train_step(
+      self._h, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), float(g_scale), grads.data_ptr(), opt.mu.data_ptr(),
+      opt.nu.data_ptr(), opt.count.data_ptr(), opt.lr, opt.b1, opt.b2, opt.eps, _ptr(loss_out), ws.data_ptr(), n, B)
   _abi.check(st, "surj_train_step")
 
 
@@ -175,11 +201,12 @@ def _plan_train_step_dp(self, dp, y, x, flat, g_scale, grads, opt, loss_out):
   """surj_train_step_dp: the same two launches with the sum over ranks fused in (NVLink peer mailboxes)."""
   B = y.shape[0]
   _check_inputs(self, y, x, flat)
-  ws, n = self.workspace(B, True, y.device)
-  st = self._lib.surj_train_step_dp(
-    self._h, dp.handle, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), float(g_scale), grads.data_ptr(),
-    opt.mu.data_ptr(), opt.nu.data_ptr(), opt.count.data_ptr(), opt.lr, opt.b1, opt.b2, opt.eps, _ptr(loss_out),
-    ws.data_ptr(), n, B)
+  with _on(y):
+    ws, n = self.workspace(B, True, y.device)
+    st = self._lib.surj_train_step_dp(
+      self._h, dp.handle, _stream(y), y.data_ptr(), _ptr(x), flat.data_ptr(), float(g_scale), grads.data_ptr(),
+      opt.mu.data_ptr(), opt.nu.data_ptr(), opt.count.data_ptr(), opt.lr, opt.b1, opt.b2, opt.eps, _ptr(loss_out),
+      ws.data_ptr(), n, B)
   _abi.check(st, "surj_train_step_dp")
 
 
@@ -208,9 +235,13 @@ def _check_inputs(plan, y, x, flat):
     raise ValueError("flat parameter buffer does not match the plan")
 
 
-def get_plan(spec: ChainSpec, base=BASE_STANDARD_NORMAL, mode=None) -> Plan:
+def get_plan(spec: ChainSpec, base=BASE_STANDARD_NORMAL, mode=None, device=None) -> Plan:
+  """The plan of (chain, base, executor) ON `device`: the C plan keeps device-resident tables and per-device launch
+  facts, so the cache is keyed by the device index as well (the same chain on cuda:1 gets its own plan)."""
   mode = _default_mode if mode is None else mode
-  key = (spec.structure(), base, mode)
+  dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+  idx = dev.index if dev.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+  key = (spec.structure(), base, mode, idx)
   with _plans_lock:
     plan = _plans.get(key)
     if plan is None:
@@ -273,7 +304,7 @@ def run_transform(transform, y, x, honour_x=True, base=None):
             torch.zeros(B, dtype=torch.float32, device=y.device))
   if not y.is_cuda:
     raise _abi.SurjError("surjectors_b200 computes on CUDA tensors only (there is no CPU fallback)")
-  plan = get_plan(spec, BASE_STANDARD_NORMAL if base is not None else BASE_NONE)
+  plan = get_plan(spec, BASE_STANDARD_NORMAL if base is not None else BASE_NONE, device=y.device)
   flat = hk.pack_params(fr.params, fr.layout, y.device)
   xx = x if dx > 0 else None
   if torch.is_grad_enabled() and (flat.requires_grad or y.requires_grad or (xx is not None and xx.requires_grad)):
@@ -302,7 +333,9 @@ def run_forward(transform, z, x, honour_x=True, eps=None):
     B = z.shape[0]
     return (torch.zeros((B, d_in), dtype=torch.float32, device=z.device),
             torch.zeros(B, dtype=torch.float32, device=z.device))
-  plan = get_plan(spec, BASE_NONE)
+  if not z.is_cuda:
+    raise _abi.SurjError("surjectors_b200 computes on CUDA tensors only (there is no CPU fallback)")
+  plan = get_plan(spec, BASE_NONE, device=z.device)
   flat = hk.pack_params(fr.params, fr.layout, z.device)
   n_eps = plan.noise_dim()
   if n_eps > 0 and eps is None:

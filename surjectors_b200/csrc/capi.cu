@@ -3,6 +3,7 @@
 // reduction and the fused Adam update.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -351,11 +352,22 @@ extern "C" int32_t surj_plan_is_fused(const SurjPlan* plan) {
 }
 extern "C" int32_t surj_plan_dim_out(const SurjPlan* plan) { return plan ? plan->dim_out : -1; }
 
+// A plan is bound to the device that is current at its first launch: its staging tables are allocated there and
+// its occupancy facts are that device's.  Calls from any other device are refused instead of dereferencing another
+// GPU's tables (one plan per device: the host layer keys its plan cache by device).
 static int ensure_device(const SurjPlan* p) {
-  if (p->dev_ready) return SURJ_OK;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return surj_cuda_fail(e, "cudaGetDevice");
+  if (p->dev_ready) {
+    if (dev != p->device) {
+      surj_set_error("plan is bound to CUDA device " + std::to_string(p->device) + " but device " + std::to_string(dev) +
+                     " is current: create one plan per device");
+      return SURJ_E_INVALID;
+    }
+    return SURJ_OK;
+  }
+  p->device = dev;
   e = cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return surj_cuda_fail(e, "cudaDeviceGetAttribute");
   if (p->exec == 2 || p->exec == 3) {
@@ -479,7 +491,9 @@ struct DpArgs {
   unsigned long long* const* peer_box;  // [world] device pointers to the peers' mailboxes (nullptr: single GPU)
   unsigned long long* my_box;
   int rank, world;
-  int* err;                     // set to 1 if a peer did not arrive in time
+  int* err;                     // device flag, sticky: 1 once a peer did not arrive in time -- every later step is a no-op
+  int* err_host;                // host-mapped mirror of the flag (the host polls it without synchronising)
+  long long timeout_cycles;     // 0: wait for ever (what NCCL does)
 };
 constexpr int RSL = 8;
 
@@ -533,7 +547,13 @@ surj_reduce_partials_kernel(const float* __restrict__ partials, int nrows, int n
 #pragma unroll
         for (int k = 0; k < RSL; ++k) g += __ldcg(slices + (size_t)k * npad + col);
       }
+      bool dp_fail = false;
       if (multi) {
+        // A step whose exchange timed out must not touch the replicated state: it would add a stale mailbox value and
+        // let the replicas drift apart silently.  The flag is sticky, the update and the step counter are skipped for
+        // this and every later step, and the host raises on its next poll (TrainStep.check / surj_dp_error).
+        const bool dead = *reinterpret_cast<volatile int*>(dp.err) != 0;
+        bool late = false;
         // Data parallel: this warp finishes its 32 columns across ALL ranks.  My shard's sums go straight into every
         // rank's mailbox (NVLink peer stores); value and step tag travel in ONE aligned 8-byte store, so a value is
         // usable the moment it is visible (no fence + separate flag round trip).  The peers' contributions are summed
@@ -541,7 +561,7 @@ surj_reduce_partials_kernel(const float* __restrict__ partials, int nrows, int n
         // parity: a rank can be at most one step ahead of the slowest.
         const unsigned t = (unsigned)(*ad.count + 1);
         const int buf = (int)(t & 1u);
-        if (valid) {
+        if (valid && !dead) {
           const size_t slot = ((size_t)buf * dp.world + dp.rank) * npad + col;
           const unsigned long long packed = ((unsigned long long)t << 32) | (unsigned long long)__float_as_uint(g);
           for (int p = 0; p < dp.world; ++p) reinterpret_cast<volatile unsigned long long*>(dp.peer_box[p])[slot] = packed;
@@ -552,18 +572,25 @@ surj_reduce_partials_kernel(const float* __restrict__ partials, int nrows, int n
             unsigned long long v = *src;
             const long long t0 = clock64();
             while ((unsigned)(v >> 32) != t) {
-              if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone; report instead of hanging the GPU
-                *dp.err = 1;
+              if (dp.timeout_cycles > 0 && clock64() - t0 > dp.timeout_cycles) {  // a peer is gone: report, do not hang
+                late = true;
                 break;
               }
               v = *src;
             }
+            if (late) break;
             g += __uint_as_float((unsigned)v);
           }
         }
         __syncwarp();
+        dp_fail = dead || __any_sync(0xffffffffu, late);
+        if (dp_fail && lane == 0 && !dead) {
+          *reinterpret_cast<volatile int*>(dp.err) = 1;
+          *reinterpret_cast<volatile int*>(dp.err_host) = 1;
+          __threadfence_system();
+        }
       }
-      if (valid) {
+      if (valid && !dp_fail) {
         if (col < np) {
           g_params[col] = g;
           if (ad.params != nullptr) adam_update(ad, col, g, *ad.count + 1);  // optax.adam
@@ -574,7 +601,9 @@ surj_reduce_partials_kernel(const float* __restrict__ partials, int nrows, int n
       __threadfence();
       if (lane == 0) {
         const unsigned done = atomicAdd(tickets + gridDim.x, 1u);
-        if (done == gridDim.x - 1 && ad.params != nullptr) *ad.count += 1;  // every column block has read count
+        // every column block has read count; a failed exchange (any column block of this step) leaves it where it was
+        if (done == gridDim.x - 1 && ad.params != nullptr && !(multi && *reinterpret_cast<volatile int*>(dp.err) != 0))
+          *ad.count += 1;
       }
     }
   }
@@ -756,8 +785,19 @@ struct SurjDp {
   SurjSlot* box = nullptr;       // [2][world][npad]
   std::vector<void*> opened;     // peers' mappings (cudaIpcOpenMemHandle)
   SurjSlot** d_peer_box = nullptr;
-  int* d_err = nullptr;
+  int* d_err = nullptr;          // sticky device flag
+  int* h_err = nullptr;          // pinned, host-mapped mirror (cudaHostAllocMapped)
+  int* h_err_dev = nullptr;      // device pointer of the mirror
+  long long timeout_cycles = 0;  // 0 = wait for ever
+  int device = 0;
 };
+
+static long long dp_cycles_of_ms(int device, long long ms) {
+  if (ms <= 0) return 0;
+  int khz = 1965000;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  return ms * (long long)khz;
+}
 
 extern "C" int surj_dp_create(int32_t rank, int32_t world, int64_t n_params, SurjDp** out, unsigned char* handle_out) {
   if (!out || !handle_out || world < 1 || rank < 0 || rank >= world || n_params <= 0) {
@@ -772,7 +812,14 @@ extern "C" int surj_dp_create(int32_t rank, int32_t world, int64_t n_params, Sur
   if (e == cudaSuccess) e = cudaMemset(d->box, 0, bytes);  // tag 0: no step has been delivered
   if (e == cudaSuccess) e = cudaMalloc((void**)&d->d_err, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(d->d_err, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&d->h_err, sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) { *d->h_err = 0; e = cudaHostGetDevicePointer((void**)&d->h_err_dev, d->h_err, 0); }
+  if (e == cudaSuccess) e = cudaGetDevice(&d->device);
   if (e != cudaSuccess) { delete d; return surj_cuda_fail(e, "surj_dp_create"); }
+  {  // default 30 s; SURJ_B200_DP_TIMEOUT_MS=0 waits for ever like a NCCL collective
+    const char* env = getenv("SURJ_B200_DP_TIMEOUT_MS");
+    d->timeout_cycles = dp_cycles_of_ms(d->device, env ? atoll(env) : 30000ll);
+  }
   cudaIpcMemHandle_t h;
   e = cudaIpcGetMemHandle(&h, d->box);
   if (e != cudaSuccess) { delete d; return surj_cuda_fail(e, "cudaIpcGetMemHandle"); }
@@ -806,6 +853,7 @@ extern "C" void surj_dp_destroy(SurjDp* d) {
   for (void* p : d->opened) cudaIpcCloseMemHandle(p);
   if (d->d_peer_box) cudaFree(d->d_peer_box);
   if (d->d_err) cudaFree(d->d_err);
+  if (d->h_err) cudaFreeHost(d->h_err);
   if (d->box) cudaFree(d->box);
   delete d;
 }
@@ -814,6 +862,17 @@ extern "C" int32_t surj_dp_error(const SurjDp* d) {  // synchronises: for tests 
   int v = 0;
   if (d && d->d_err) cudaMemcpy(&v, d->d_err, sizeof v, cudaMemcpyDeviceToHost);
   return v;
+}
+
+// Non-blocking: reads the host-mapped mirror of the flag.  Cheap enough to poll before every step.
+extern "C" int32_t surj_dp_error_nosync(const SurjDp* d) {
+  return (d && d->h_err) ? *reinterpret_cast<volatile int*>(d->h_err) : 0;
+}
+
+extern "C" int surj_dp_set_timeout_ms(SurjDp* d, int64_t ms) {
+  if (!d || ms < 0) { surj_set_error("surj_dp_set_timeout_ms: bad arguments"); return SURJ_E_INVALID; }
+  d->timeout_cycles = dp_cycles_of_ms(d->device, (long long)ms);
+  return SURJ_OK;
 }
 
 extern "C" int surj_train_step_dp(const SurjPlan* plan, SurjDp* d, SurjStream stream, const float* y, const float* x,
@@ -834,7 +893,7 @@ extern "C" int surj_train_step_dp(const SurjPlan* plan, SurjDp* d, SurjStream st
     surj_set_error("SurjDp was created for a different parameter count");
     return SURJ_E_INVALID;
   }
-  DpArgs dp{d->d_peer_box, d->box, d->rank, d->world, d->d_err};
+  DpArgs dp{d->d_peer_box, d->box, d->rank, d->world, d->d_err, d->h_err_dev, d->timeout_cycles};
   return fused_backward(plan, (cudaStream_t)stream, y, x, params, nullptr, g_scale, nullptr, g_params, loss_out, nullptr,
                         nullptr, nullptr, workspace, workspace_bytes, batch, AdamArgs{params, mu, nu, count, lr, b1, b2, eps},
                         dp);

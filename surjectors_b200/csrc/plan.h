@@ -22,6 +22,7 @@ struct SurjPlan {
   struct CcPlan* ccp = nullptr;         // compact looped kernel for affine coupling / funnel chains (compact.cuh)
   // lazily filled device facts
   mutable bool dev_ready = false;
+  mutable int device = -1;  // the device the plan was first used on (ensure_device)
   mutable int n_sm = 148, fwd_blocks = 4, bwd_blocks = 2;
   int exec = 0;  // 1 generated straight-line kernel, 2 fused interpreter kernel, 3 per-op executor, 4 compact looped kernel
 };

@@ -9,14 +9,70 @@
 // Runs of per-sample ops between them execute in one vg_elem launch.  Parameters are compacted /
 // masked / transposed once per call by vg_stage into the workspace (the staging table of the plan).
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
+#include <string>
+#include <vector>
 
 #include "plan.h"
 #include "vm_ops.cuh"
 #include "vm_plan.h"
 #include "vm_tc.cuh"
+
+// ---- per-kernel timing (surj_profile_begin / surj_profile_end): every launch of the executor bracketed by events
+namespace prof {
+enum Kind { LINEAR_TC = 0, LINEAR_SIMT, DW_TC, DW_SIMT, ELEM, TILE, STAGE, N_KINDS };
+const char* const kNames[N_KINDS] = {"linear_tcgen05", "linear_simt", "dw_tcgen05", "dw_simt", "per_sample_ops", "operand_tiling",
+                                     "staging_writeback"};
+struct Rec { int kind; double flops; cudaEvent_t a, b; };
+bool g_on = false;
+std::vector<Rec> g_recs;
+struct Scope {
+  cudaStream_t st; bool on;
+  Scope(cudaStream_t s, int kind, double flops) : st(s), on(g_on) {
+    if (!on) return;
+    Rec r{kind, flops, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_recs.push_back(r);
+  }
+  ~Scope() { if (on) cudaEventRecord(g_recs.back().b, st); }
+};
+}  // namespace prof
+
+extern "C" int surj_profile_begin(void) {
+  for (auto& r : prof::g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  prof::g_recs.clear();
+  prof::g_on = true;
+  return SURJ_OK;
+}
+extern "C" int64_t surj_profile_end(char* out, int64_t out_bytes) {
+  if (!prof::g_on) return 0;
+  prof::g_on = false;
+  cudaDeviceSynchronize();
+  double ms[prof::N_KINDS] = {0}, fl[prof::N_KINDS] = {0};
+  long long n[prof::N_KINDS] = {0};
+  for (auto& r : prof::g_recs) {
+    float t = 0.0f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[r.kind] += t; fl[r.kind] += r.flops; n[r.kind] += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  prof::g_recs.clear();
+  std::string js = "{";
+  for (int k = 0; k < prof::N_KINDS; ++k) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e}", k ? ", " : "", prof::kNames[k], n[k], ms[k], fl[k]);
+    js += buf;
+  }
+  js += "}";
+  if (!out || (int64_t)js.size() + 1 > out_bytes) return 0;
+  memcpy(out, js.c_str(), js.size() + 1);
+  return (int64_t)js.size();
+}
 
 namespace vm {
 
@@ -230,11 +286,15 @@ vg_writeback(const int32_t* __restrict__ grad_dst, const int32_t* __restrict__ g
 // ------------------------------------------------------------------------------ host
 namespace {
 inline size_t a256(size_t n) { return (n + 255) & ~(size_t)255; }
+// chunk width target: SURJ_B200_CHUNK at load time, surj_set_chunk_samples() afterwards (tests run multi-chunk cases
+// at oracle-sized batches with it; 0 restores the default)
+constexpr int64_t kDefaultChunk = 131072;
+std::atomic<int64_t> g_chunk_target{[] { const char* e = getenv("SURJ_B200_CHUNK"); return e ? atoll(e) : kDefaultChunk; }()};
 inline int chunk_cols(int64_t B, int n_rows) {
   // rows of one chunk must stay within 8 GB; the target width trades L2 residency between kernels (small chunks)
   // against resident threads in the per-sample kernels and grid sizes of the tiles (large chunks).  Measured at batch
   // 262144 (cfg4 / cfg5 train step, ms): 16384: 629 / 729, 65536: 515 / 494, 131072: 499 / 474, 262144: 499 / 463.
-  static const int64_t target = [] { const char* e = getenv("SURJ_B200_CHUNK"); return e ? atoll(e) : 131072ll; }();
+  const int64_t target = g_chunk_target.load(std::memory_order_relaxed);
   int64_t c = std::min<int64_t>(target, (B + 127) / 128 * 128);
   const int64_t cap = ((int64_t)8192 << 20) / ((int64_t)n_rows * 4) / 128 * 128;
   c = std::max<int64_t>(128, std::min(c, cap));
@@ -263,6 +323,20 @@ const VmTcInfo& tc_info(const VmPlan* v, int prog) {
     t.max_kpad = std::max(t.max_kpad, nkb * vmtc::PBK);
   }
   // structural zeros at tile granularity, read off the gather table (masked weights are STAGE_ZERO)
+  // structurally non-zero weights per matrix op (needed FLOPs per sample = 2 x this), read off the gather table
+  t.nnz.assign(ops.size(), 0.0);
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const vm::Op& op = ops[i];
+    int w_off, ld, n_in, n_out;
+    if (op.code == vm::OP_LINEAR) { w_off = op.a[2]; ld = op.a[3]; n_in = op.a[1]; n_out = op.a[12]; }
+    else if (op.code == vm::OP_LINEAR_DW) { w_off = op.a[4]; ld = op.a[5]; n_in = op.a[1]; n_out = op.a[3]; }
+    else continue;
+    double c = 0.0;
+    for (int a = 0; a < n_in; ++a)
+      for (int b = 0; b < n_out; ++b)
+        if (v->stage[(size_t)w_off + (size_t)a * ld + b] != vm::STAGE_ZERO) c += 1.0;
+    t.nnz[i] = c;
+  }
   t.kr.assign(ops.size(), VmKRange{});
   t.dw_skip.assign(ops.size(), 0ull);
   for (size_t i = 0; i < ops.size(); ++i) {
@@ -327,6 +401,12 @@ Carve carve(const VmPlan* v, void* ws, int C, int prog) {
 }
 }  // namespace
 
+extern "C" int64_t surj_set_chunk_samples(int64_t samples) {
+  const int64_t prev = g_chunk_target.load();
+  g_chunk_target.store(samples > 0 ? (samples + 127) / 128 * 128 : kDefaultChunk);
+  return prev;
+}
+
 size_t vm_global_workspace_bytes(const VmPlan* v, int64_t B, bool backward) {
   const int C = chunk_cols(B, v->n_rows);
   if (backward) return carve(v, nullptr, C, VM_PROG_BWD).total;
@@ -385,10 +465,13 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   io.g_scale = g_scale; io.with_base = with_base; io.backward = backward ? 1 : 0;
   io.eps = eps; io.n_eps = v->n_eps;
 
-  vm::vg_stage<<<std::min((n_par + 255) / 256, 148 * 8), 256, 0, st>>>(P.stage, n_par, params, k.par, k.grad, backward ? 1 : 0,
-                                                                      k.scal_g, v->n_scalars, k.loss);
-  if (!v->sjobs.empty())
-    vm::vg_scalars<<<((int)v->sjobs.size() + 31) / 32, 32, 0, st>>>(P.sjobs, (int)v->sjobs.size(), k.par, k.scal);
+  {
+    prof::Scope ps(st, prof::STAGE, 0.0);
+    vm::vg_stage<<<std::min((n_par + 255) / 256, 148 * 8), 256, 0, st>>>(P.stage, n_par, params, k.par, k.grad, backward ? 1 : 0,
+                                                                        k.scal_g, v->n_scalars, k.loss);
+    if (!v->sjobs.empty())
+      vm::vg_scalars<<<((int)v->sjobs.size() + 31) / 32, 32, 0, st>>>(P.sjobs, (int)v->sjobs.size(), k.par, k.scal);
+  }
   // tensor-core LINEAR ops: split (hi / lo TF32) and tile every weight matrix they use, once per call
   const VmTcInfo& tci = tc_info(v, prog);
   // Default: the TMA-fed pipelined kernel on pre-tiled operands.  It is L2-bandwidth bound (hi + lo planes of both
@@ -403,6 +486,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
       done[tci.w_off[i]] = true;
       const vm::Op& op = ops[i];
       dim3 grid((op.a[12] + vmtc::TM - 1) / vmtc::TM, (op.a[1] + 31) / 32);
+      prof::Scope ps(st, prof::TILE, 0.0);
       vmtc::vg_tile<false><<<grid, 256, 0, st>>>(k.par + op.a[10], (size_t)op.a[11], op.a[12], op.a[1],
                                                  (op.a[1] + vmtc::PBK - 1) / vmtc::PBK, k.w_tiles + tci.w_off[i]);
     }
@@ -414,23 +498,29 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
     while (pc < ops.size()) {
       const vm::Op& op = ops[pc];
       if (op.code == vm::OP_LINEAR) {
+        const double fl = 2.0 * tci.nnz[pc] * (double)cols;
         if (pipe && tci.w_off[pc] >= 0) {  // tcgen05 3xTF32, TMA-fed pipeline on pre-tiled operands
           const int nkb = (op.a[1] + vmtc::PBK - 1) / vmtc::PBK;
+          { prof::Scope ps(st, prof::TILE, 0.0);
           vmtc::vg_tile<true><<<dim3(cols / vmtc::TM, (op.a[1] + 31) / 32), 256, 0, st>>>(k.rows + (size_t)op.a[0] * C, (size_t)C,
-                                                                                       cols, op.a[1], nkb, k.a_tiles);
+                                                                                       cols, op.a[1], nkb, k.a_tiles); }
           dim3 grid(cols / vmtc::TM, (op.a[5] + vmtc::TN - 1) / vmtc::TN);
+          prof::Scope ps(st, prof::LINEAR_TC, fl);
           vmtc::vg_linear_pipe<<<grid, vmtc::PIPE_THREADS, vmtc::PIPE_SMEM, st>>>(op, k.rows, C, k.par, k.a_tiles,
                                                                                  k.w_tiles + tci.w_off[pc], nkb, tci.kr[pc]);
         } else if (use_tc && use_tc_lin && tc_linear_op(op)) {  // register-staged tcgen05 kernel
           dim3 grid(cols / vmtc::TM, (op.a[5] + vmtc::TN - 1) / vmtc::TN);
+          prof::Scope ps(st, prof::LINEAR_TC, fl);
           vmtc::vg_linear_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, k.par);
         } else {
           dim3 grid(cols / vm::LBM, (op.a[5] + vm::LBN - 1) / vm::LBN);
+          prof::Scope ps(st, prof::LINEAR_SIMT, fl);
           vm::vg_linear<<<grid, 256, 0, st>>>(op, k.rows, C, k.par);
         }
         ++pc;
       } else if (op.code == vm::OP_LINEAR_DW) {
         const int NA = op.a[1] + (op.a[6] >= 0 ? 1 : 0), NG = op.a[3];
+        const double fl = 2.0 * tci.nnz[pc] * (double)cols;
         if (use_tc && use_tc_dw && NA >= 32 && NG >= 32) {
           // sample slabs sized so the grid fills the machine about twice (2 CTAs per SM x 148 SMs x 2)
           // (the bias gradient comes out of staging the g operand, so the tile rows cover the n_in real inputs only)
@@ -439,16 +529,19 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           const int want = std::max(1, (592 + tiles - 1) / tiles);
           const int slab = std::max(512, (cols / want) / 128 * 128);
           dim3 grid(ti, (NG + vmtc::TN - 1) / vmtc::TN, (cols + slab - 1) / slab);
+          prof::Scope ps(st, prof::DW_TC, fl);
           vmtc::vg_dw_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, cols, slab, k.grad, tci.dw_skip[pc]);
         } else {
           const int slab = 2048;
           dim3 grid((NA + vm::DBI - 1) / vm::DBI, (NG + vm::DBJ - 1) / vm::DBJ, (cols + slab - 1) / slab);
+          prof::Scope ps(st, prof::DW_SIMT, fl);
           vm::vg_dw<<<grid, 256, 0, st>>>(op, k.rows, C, cols, slab, k.grad);
         }
         ++pc;
       } else {
         size_t e = pc;
         while (e < ops.size() && ops[e].code != vm::OP_LINEAR && ops[e].code != vm::OP_LINEAR_DW) ++e;
+        prof::Scope ps(st, prof::ELEM, 0.0);
         vm::vg_elem<<<cols / 128, 128, 0, st>>>(d_ops + pc, (int)(e - pc), first ? 1 : 0, io, k.rows, C, base, B, P.itab,
                                               k.scal, k.scal_g, k.loss);
         first = false;
@@ -459,11 +552,102 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   if (backward) {
     cudaError_t e = cudaMemsetAsync(g_params, 0, (size_t)v->n_params * 4, st);
     if (e != cudaSuccess) return surj_cuda_fail(e, "cudaMemsetAsync(g_params)");
+    prof::Scope ps(st, prof::STAGE, 0.0);
     vm::vg_writeback<<<std::min((n_par + 255) / 256, 148 * 8), 256, 0, st>>>(
         P.grad_dst, P.grad_aux, n_par, k.grad, k.par, k.scal_g, params, g_params, k.loss, loss_out,
         g_lp ? 1.0f : g_scale);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return surj_cuda_fail(e, "per-layer path launch");
+  return SURJ_OK;
+}
+
+// ------------------------------------------------------------- TF32 tensor-pipe peak probe
+// Measurement helper (bench.py): the dense TF32 tcgen05.mma rate of this GPU -- the denominator of roofline.frac for the
+// wide-network path ("3xTF32: three TF32 MMAs per FP32-grade product, so peak / 3").  One CTA per SM issues
+// `iters` x 4 MMAs of M=128 x N=256 x K=8 (kind::tf32, A from tensor memory, B from shared memory: the operand sourcing
+// the product kernel uses; measured 1.04 PFLOP/s on B200, tools/ubench/tc_probe.cu has the shared-memory-A variants).
+namespace {
+using namespace vmtc;
+
+constexpr int PKN = 256;
+constexpr size_t PK_SMEM = (size_t)PKN * 32 * 4 + 1024 + 64;
+
+__global__ void __launch_bounds__(128) surj_tf32_peak_kernel(int iters, float* __restrict__ sink) {
+  extern __shared__ unsigned char raw[];
+  float* b = (float*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = (uint64_t*)(b + PKN * 32);
+  uint32_t* slot = (uint32_t*)(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < PKN * 32; i += 128) b[i] = 0.5f - (float)(i & 3) * 0.25f;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t0 = *slot;
+  const uint32_t a_col = 480;  // A block (K = 32) at columns [480, 512), D at [0, 256)
+  {
+    uint32_t v = __float_as_uint(1.0f + 0.125f * (float)(tid & 7));
+    for (int k = 0; k < 32; k += 4)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(t0 + ((uint32_t)(warp * 32) << 16) + a_col + k), "r"(v)
+                   : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint64_t db = make_desc(smem_u32(b));
+    const uint32_t id = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PKN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+            "}\n" ::"r"(t0), "r"(t0 + a_col + ks * 8), "l"(db + (uint64_t)(ks * 16)), "r"(id), "r"(1u)
+            : "memory");
+    }
+    umma_commit(bar);
+  }
+  if (tid < 32) mbar_wait(bar, 0);
+  __syncthreads();
+  tc_fence_after();
+  float v[32];
+  tmem_ld32(t0 + ((uint32_t)(warp * 32) << 16), v);
+  if (v[0] == 123.456f) sink[0] = v[1];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(512) : "memory");
+}
+}  // namespace
+
+extern "C" int surj_bench_tf32_peak(SurjStream stream, int32_t iters, float* sink, double* flops_out) {
+  if (!sink || iters <= 0) {
+    surj_set_error("surj_bench_tf32_peak: bad arguments");
+    return SURJ_E_INVALID;
+  }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(surj_tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
+    if (e != cudaSuccess) return surj_cuda_fail(e, "cudaFuncSetAttribute(tf32 peak probe)");
+    attr = true;
+  }
+  surj_tf32_peak_kernel<<<n_sm, 128, PK_SMEM, (cudaStream_t)stream>>>(iters, sink);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return surj_cuda_fail(e, "tf32 peak probe launch");
+  if (flops_out) *flops_out = (double)n_sm * iters * 4.0 * 128.0 * PKN * 8.0 * 2.0;
   return SURJ_OK;
 }

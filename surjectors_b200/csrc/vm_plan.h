@@ -18,6 +18,7 @@ struct VmTcInfo {
   bool ready = false;
   std::vector<VmKRange> kr;                // per op (LINEAR on the pipelined kernel)
   std::vector<unsigned long long> dw_skip; // per op (LINEAR_DW): bit (i_tile * n_j_tiles + j_tile) set = all-zero tile
+  std::vector<double> nnz;                 // per op (LINEAR / LINEAR_DW): structurally non-zero weights of its matrix
   std::vector<long long> w_off;  // per op: float offset of its tiled [out][in] weights inside the weight-tile region, -1 = not a tensor-core op
   size_t w_floats = 0;           // size of the weight-tile region
   int max_kpad = 0;              // max over tensor-core ops of n_in rounded up to 32 (activation tiles need kpad * 2 floats per sample)

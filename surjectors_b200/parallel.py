@@ -30,6 +30,25 @@ def adam_reference_(p, g, mu, nu, t, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
   return p
 
 
+def peer_access_everywhere(device, group=None):
+  """True on every rank iff all ranks sit on one host and every rank's GPU can map every other rank's GPU
+  (cudaDeviceCanAccessPeer).  Collective: all ranks must call it; all get the same answer."""
+  import socket
+
+  me = (socket.gethostname(), torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device())
+  world = dist.get_world_size(group)
+  everyone = [None] * world
+  dist.all_gather_object(everyone, me, group=group)
+  ok = len({h for h, _ in everyone}) == 1
+  if ok:
+    for _, idx in everyone:
+      if idx != me[1] and not torch.cuda.can_device_access_peer(me[1], idx):
+        ok = False
+  flags = [None] * world
+  dist.all_gather_object(flags, bool(ok), group=group)
+  return all(flags)
+
+
 class PeerExchange:
   """The fused alternative to the all-reduce for KB-sized gradients: every rank's reduced gradient is stored
   straight into its peers' mailboxes over NVLink peer memory by the gradient-reduction kernel itself, which
@@ -56,7 +75,18 @@ class PeerExchange:
     return self._h
 
   def error(self):
+    """Synchronising read of the device-side error flag."""
     return int(self._lib.surj_dp_error(self._h))
+
+  def error_nosync(self):
+    """Non-blocking poll (host-mapped flag): 1 once a peer missed the exchange timeout."""
+    return int(self._lib.surj_dp_error_nosync(self._h))
+
+  def set_timeout_ms(self, ms):
+    """0 = wait for ever (what a NCCL collective does); default 30 s (SURJ_B200_DP_TIMEOUT_MS)."""
+    from surjectors_b200 import _abi
+
+    _abi.check(self._lib.surj_dp_set_timeout_ms(self._h, int(ms)), "surj_dp_set_timeout_ms")
 
   def close(self):
     if self._h:

@@ -45,11 +45,11 @@ class TrainStep:
     if layout.signature() != params.layout.signature():
       raise ValueError("params do not belong to this model")
     self.spec = traced[0]
-    self.plan = _runtime.get_plan(self.spec)
     self.params = params
     self.flat = params.flat
     if not self.flat.is_cuda:
       raise _abi.SurjError("TrainStep needs parameters on a CUDA device (there is no CPU fallback)")
+    self.plan = _runtime.get_plan(self.spec, device=self.flat.device)
     self.opt = Adam(self.flat, lr, b1, b2, eps)
     self.grads = torch.zeros(self.flat.numel() + 4, dtype=torch.float32, device=self.flat.device)
     self.reduction = reduction
@@ -64,9 +64,14 @@ class TrainStep:
       self.world = dist.get_world_size(process_group)
       # KB-sized gradients: exchange fused into the reduction kernel over NVLink peer memory; large ones
       # (wide networks, per-op executor): one NCCL all-reduce.  SURJ_B200_EXCHANGE=nccl forces the latter.
+      # The peer exchange needs every rank on one node with CUDA peer access to every other rank's GPU; the probe is
+      # collective, so all ranks take the same branch (anything else falls back to the all-reduce).
       if (self.world > 1 and self.plan.is_fused and self.flat.numel() <= (1 << 16)
-          and os.environ.get("SURJ_B200_EXCHANGE", "peer") != "nccl"):
-        self.peer = parallel.PeerExchange(self.flat.numel(), process_group)
+          and os.environ.get("SURJ_B200_EXCHANGE", "peer") != "nccl"
+          and parallel.peer_access_everywhere(self.flat.device, process_group)):
+        with torch.cuda.device(self.flat.device):
+          self.peer = parallel.PeerExchange(self.flat.numel(), process_group)
+    self._global_batch = {}
 
   @property
   def loss(self):
@@ -78,10 +83,31 @@ class TrainStep:
       return 2
     return self.plan.launches(backward=True) + 2 + (1 if self.world > 1 else 0)
 
+  def check(self):
+    """Raise if the data-parallel exchange reported a peer that never arrived (non-blocking poll of a host-mapped
+    flag).  A failed step leaves parameters, moments and the step counter untouched on this rank."""
+    if self.peer is not None and self.peer.error_nosync():
+      raise _abi.SurjError("data-parallel exchange timed out: a peer rank did not deliver its gradient "
+                           "(no update was applied on this rank since); stop and restart from a checkpoint")
+
+  def _mean_scale(self, B):
+    """-1 / (global sample count): shards made by shard_bounds differ by up to one sample, so the local batch times
+    the world size is not the global batch.  One all-reduce per distinct local batch size, cached."""
+    if self.world == 1:
+      return -1.0 / B
+    if B not in self._global_batch:
+      import torch.distributed as dist
+
+      t = torch.tensor([B], dtype=torch.int64, device=self.flat.device)
+      dist.all_reduce(t, group=self.group)
+      self._global_batch[B] = int(t.item())
+    return -1.0 / self._global_batch[B]
+
   def step(self, y, x=None):
     n = self.flat.numel()
     B = y.shape[0]
-    g_scale = -1.0 if self.reduction == "sum" else -1.0 / (B * self.world)
+    self.check()
+    g_scale = -1.0 if self.reduction == "sum" else self._mean_scale(B)
     xx = x if self.plan.dim_x > 0 else None
     if self.world == 1:  # the whole step is two launches: backward kernel, reduction + Adam
       self.plan.train_step(y, xx, self.flat, g_scale, self.grads, self.opt, self.grads[n:n + 1])
@@ -97,7 +123,9 @@ class TrainStep:
 
   # ---- host-fed steps: the batch lives in (pinned) host memory, the loss is read back
   def _staging(self, y_host, x_host):
-    if getattr(self, "_stage", None) is None or self._stage[0][0].shape != y_host.shape:
+    shapes = (tuple(y_host.shape), None if x_host is None else tuple(x_host.shape))
+    if getattr(self, "_stage", None) is None or self._stage_shapes != shapes:
+      self._stage_shapes = shapes
       dev = self.flat.device
       self._copy_stream = torch.cuda.Stream(dev)
       self._stage = []
@@ -111,7 +139,8 @@ class TrainStep:
   def step_host(self, y_host, x_host=None, loss_out=None):
     """One step on a host batch: H2D copy on a side stream into one of two staging buffers (so the
     copy of batch i+1 overlaps the kernels of batch i), the step, and an async D2H copy of the loss
-    into `loss_out` (a pinned host tensor) if given.  Enqueue-only; call `drain()` before reading."""
+    into `loss_out` (a pinned host tensor) if given.  Enqueue-only; `drain()` blocks the host until every
+    enqueued copy (the D2H loss reads included) has completed -- call it before reading `loss_out`."""
     ys, xs, ready, free = self._staging(y_host, x_host)
     cur = torch.cuda.current_stream(self.flat.device)
     if self._n_host >= 2:
@@ -126,9 +155,16 @@ class TrainStep:
     free.record(cur)
     if loss_out is not None:
       loss_out.copy_(loss, non_blocking=True)
+    if getattr(self, "_done", None) is None:
+      self._done = torch.cuda.Event()
+    self._done.record(cur)  # after the step's kernels and its D2H loss copy
     self._n_host += 1
     return loss
 
   def drain(self):
+    """Host-blocking: returns when every host-fed step enqueued so far has finished, its loss copy included."""
     if getattr(self, "_copy_stream", None) is not None:
       torch.cuda.current_stream(self.flat.device).wait_stream(self._copy_stream)
+    if getattr(self, "_done", None) is not None:
+      self._done.synchronize()
+    self.check()

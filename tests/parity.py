@@ -3,9 +3,13 @@
 parameters and inputs.  TEST INFRASTRUCTURE: the only place product and oracle meet.
 
 Tolerances (BASELINE.json north_star): log-probs within 1e-5 relative, gradients within 1e-4
-relative, FP32.  "Relative" is measured against max(1, |reference|) for log-probs (per sample) and
-against max(1e-3.., max|reference|) per parameter tensor for gradients, i.e. relative to the scale of
-the tensor, so exact zeros (masked MADE weights) must come out as exact zeros.
+relative, FP32.  "Relative" is measured against max(1, |reference|) for log-probs (per sample: log-probs
+are O(10)-O(100) sums, the floor only matters for the rare sample whose terms cancel) and, for gradients, per
+parameter tensor against that tensor's own max|reference| -- a TRUE relative bound -- with a floor of
+GRAD_FLOOR x the largest gradient entry of the whole model (a tensor whose gradient is a million times smaller
+than the model's is compared at the model's float32 noise level, not at its own).  Exact zeros (masked MADE
+weights) must come out as exact zeros.  Samples whose ReLU pre-activations sit within 2e-5 of the kink are left
+out of the gradient comparison; their number is bounded (KINK_MAX_FRAC of the batch).
 """
 
 import numpy as np
@@ -20,6 +24,8 @@ from surjectors_b200 import execution_mode, value_and_grad
 
 LP_RTOL = 1e-5
 GRAD_RTOL = 1e-4
+GRAD_FLOOR = 1e-3     # per-tensor scale floor, as a fraction of the model-wide max |gradient|
+KINK_MAX_FRAC = 0.05  # at most this fraction of a batch may be dropped for sitting on a ReLU kink
 
 SMALL = {  # scaled-down shapes of the two wide configs for oracle-speed parity
   "cfg4": dict(dim=12, n_keep=4, hidden=(16, 16), n_bins=5, n_pre=2, n_post=2),
@@ -34,7 +40,7 @@ def synthetic(dim, dim_x, batch, seed, scale=1.0):
   return y, x
 
 
-def build_pair(name, batch, seed=0, w_std=0.3, **scale):
+def build_pair(name, batch, seed=0, w_std=0.3, b_val=None, literal=False, **scale):
   """(product model, product params on CPU, oracle model, oracle params f64, y, x) with equal params."""
   c = pcfg.CONFIGS[name]
   kw = dict(scale)
@@ -45,7 +51,7 @@ def build_pair(name, batch, seed=0, w_std=0.3, **scale):
   x64 = None if x is None else torch.as_tensor(x, dtype=torch.float64)
   om = ohk.without_apply_rng(ohk.transform(getattr(ocfg, "make_" + name)(**kw), dtype=torch.float64))
   ob = dict(y=y64) if x64 is None else dict(y=y64, x=x64)
-  oparams = ocfg.randomize(om.init(2000 + seed, **ob), 2000 + seed, w_std=w_std)
+  oparams = ocfg.randomize(om.init(2000 + seed, **ob), 2000 + seed, w_std=w_std, b_val=b_val, literal=literal)
   pm = phk.transform(c["make"](**kw))
   pb = dict(y=y64[:2].float()) if x64 is None else dict(y=y64[:2].float(), x=x64[:2].float())
   pparams = pm.init(2000 + seed, method="log_prob", **pb)
@@ -72,14 +78,23 @@ def lp_error(lp, ref):
   return float(np.max(np.abs(lp - ref) / np.maximum(1.0, np.abs(ref)))) if ref.size else 0.0
 
 
+def grad_scales(ref):
+  """Per-tensor comparison scale: the tensor's own max |reference gradient|, floored at GRAD_FLOOR x the model-wide max."""
+  tops = {f"{m}/{k}": (float(np.max(np.abs(np.asarray(ref[m][k].detach().cpu().double().numpy())))) if ref[m][k].numel() else 0.0)
+          for m in ref for k in ref[m]}
+  top = max(tops.values()) if tops else 0.0
+  floor = max(GRAD_FLOOR * top, 1e-30)
+  return {n: max(v, floor) for n, v in tops.items()}
+
+
 def grad_errors(grads, ref):
   out = {}
+  scales = grad_scales(ref)
   for m in ref:
     for k in ref[m]:
       g = grads[m][k].detach().cpu().double().numpy()
       r = ref[m][k].detach().cpu().double().numpy()
-      scale = max(1.0, float(np.max(np.abs(r)))) if r.size else 1.0
-      out[f"{m}/{k}"] = float(np.max(np.abs(g - r))) / scale if r.size else 0.0
+      out[f"{m}/{k}"] = float(np.max(np.abs(g - r))) / scales[f"{m}/{k}"] if r.size else 0.0
   return out
 
 
@@ -99,13 +114,35 @@ def differentiable_samples(om, oparams, ob, eps=2e-5):
   return torch.stack(probes).min(dim=0).values >= eps
 
 
-def check_config(name, batch=256, device="cuda:0", check_grad=True, seed=0, w_std=0.3, mode="auto", **scale):
+def check_config(name, batch=256, device="cuda:0", check_grad=True, seed=0, w_std=0.3, mode="auto", b_val=None,
+                 y_override=None, grad_keep=None, literal=False, kink_max_frac=KINK_MAX_FRAC, fp32_slack=False, **scale):
+  """y_override: float64 [B, dim] inputs replacing the seeded normal draws (edge cases); grad_keep: bool [B] mask of the
+  samples that take part in the gradient comparison (e.g. leave out inputs sitting exactly on a non-smooth point).
+  fp32_slack (stress cases only): the contract is parity with the reference's FLOAT32 arithmetic, the oracle is float64;
+  on ill-conditioned inputs (a spline bin 1e-3 wide amplifies a 3e-7 knot-position rounding to 1e-4 in the log-det)
+  float32 itself is further than 1e-5 from float64.  With the flag the bound per sample / per tensor becomes
+  max(LP_RTOL, 2 x the LARGEST error over the batch (log-probs) / over the parameter tensors (gradients) of the SAME
+  oracle evaluated in float32) -- never looser than twice what the reference's own precision delivers on these very
+  inputs, and reported in the result.  (The batch / model maximum rather than the per-sample value: two float32
+  evaluation orders of one sample are two draws from the same error distribution, not one draw and its double.)"""
   with execution_mode(mode):
-    return _check_config(name, batch, device, check_grad, seed, w_std, **scale)
+    return _check_config(name, batch, device, check_grad, seed, w_std, b_val, y_override, grad_keep, literal, kink_max_frac,
+                         fp32_slack, **scale)
 
 
-def _check_config(name, batch, device, check_grad, seed, w_std, **scale):
-  pm, pparams, om, oparams, y64, x64 = build_pair(name, batch, seed, w_std, **scale)
+def _oracle32(name, oparams, ob, scale):
+  om32 = ohk.without_apply_rng(ohk.transform(getattr(ocfg, "make_" + name)(**scale), dtype=torch.float32))
+  p32 = {m: {k: v.to(torch.float32) for k, v in b.items()} for m, b in oparams.items()}
+  b32 = {k: v.to(torch.float32) for k, v in ob.items()}
+  return om32, p32, b32
+
+
+def _check_config(name, batch, device, check_grad, seed, w_std, b_val=None, y_override=None, grad_keep=None, literal=False,
+                  kink_max_frac=KINK_MAX_FRAC, fp32_slack=False, **scale):
+  pm, pparams, om, oparams, y64, x64 = build_pair(name, batch, seed, w_std, b_val, literal, **scale)
+  if y_override is not None:
+    y64 = torch.as_tensor(y_override, dtype=torch.float64)
+    assert y64.shape[0] == batch
   dev = torch.device(device)
   params = to_device(pparams, dev)
   y = y64.float().to(dev)
@@ -115,13 +152,29 @@ def _check_config(name, batch, device, check_grad, seed, w_std, **scale):
   lp = pm.apply(params, None, method="log_prob", **pb)
   ref = om.apply(oparams, **ob)
   e = lp_error(lp.cpu().numpy(), ref.numpy())
-  assert np.isfinite(ref.numpy()).all()
-  assert e <= LP_RTOL, f"{name}: log_prob relative error {e:.3e} > {LP_RTOL}"
-  out = {"lp_err": e}
+  assert np.isfinite(ref.numpy()).all(), f"{name}: the float64 oracle itself is not finite on these parameters"
+  err = np.abs(lp.cpu().double().numpy() - ref.numpy()) / np.maximum(1.0, np.abs(ref.numpy()))
+  tol = np.full(err.shape, LP_RTOL)
+  slack = {}
+  if fp32_slack:
+    om32, p32, b32 = _oracle32(name, oparams, ob, scale)
+    e32 = np.abs(om32.apply(p32, **b32).double().numpy() - ref.numpy()) / np.maximum(1.0, np.abs(ref.numpy()))
+    tol = np.maximum(tol, 2.0 * float(e32.max()))
+    slack["lp_fp32_oracle_err"] = float(e32.max())
+  if (err > tol).any():
+    i = int(np.argmax(err / tol))
+    raise AssertionError(f"{name}: log_prob relative error {e:.3e} > {LP_RTOL} at sample {i}: got {float(lp[i]):.9g}, "
+                         f"ref {float(ref[i]):.12g}, y = {y64[i].numpy().tolist()}")
+  out = {"lp_err": e, **slack}
   if check_grad:
     keep = differentiable_samples(om, oparams, ob)
     if keep is not None and not bool(keep.all()):
       out["kink_samples_dropped"] = int((~keep).sum())
+      assert out["kink_samples_dropped"] <= max(2, kink_max_frac * batch), f"{name}: {out['kink_samples_dropped']} of {batch} samples on a ReLU kink"
+    if grad_keep is not None:
+      gk = torch.as_tensor(grad_keep, dtype=torch.bool)
+      keep = gk if keep is None else (keep & gk)
+    if keep is not None and not bool(keep.all()):
       ob = {k: v[keep] for k, v in ob.items()}
       pb = {k: v[keep.to(v.device)] for k, v in pb.items()}
 
@@ -133,8 +186,15 @@ def _check_config(name, batch, device, check_grad, seed, w_std, **scale):
     le = abs(float(loss) - float(oloss)) / max(1.0, abs(float(oloss)))
     assert le <= 1e-5, f"{name}: loss relative error {le:.3e}"
     ge = grad_errors(grads, ograds)
-    worst = max(ge, key=ge.get)
-    assert ge[worst] <= GRAD_RTOL, f"{name}: gradient error {ge[worst]:.3e} at {worst}"
+    gtol = {n: GRAD_RTOL for n in ge}
+    if fp32_slack:
+      om32, p32, b32 = _oracle32(name, oparams, ob, scale)
+      _, g32, _ = oad.value_and_grad(om32, p32, **b32)
+      ge32 = grad_errors(g32, ograds)
+      gtol = {n: max(GRAD_RTOL, 2.0 * max(ge32.values())) for n in ge}
+      out["grad_fp32_oracle_err"] = max(ge32.values())
+    worst = max(ge, key=lambda n: ge[n] / gtol[n])
+    assert ge[worst] <= gtol[worst], f"{name}: gradient error {ge[worst]:.3e} at {worst} (bound {gtol[worst]:.3e})"
     out["grad_err"] = ge[worst]
     out["grad_worst"] = worst
   return out

@@ -10,18 +10,44 @@ import torch
 
 from tests import parity
 from surjectors_b200 import value_and_grad
+from surjectors_b200._runtime import chunk_samples
 
 pytestmark = pytest.mark.gpu
+
+# Full-width cfg5 has 16 MADEs x 2 hidden layers x 512 ReLU units = 16 384 kinks per sample, pre-activation density near
+# zero ~1.3: P(some unit within 2e-5 of its kink) = 1 - exp(-16384 * 4e-5 * 1.3) = 57 % of the samples -- they are left
+# out of the GRADIENT comparison (float32 rounding decides the side of the kink, tests/parity.py); at least a quarter
+# of the batch must remain.  cfg4 uses swish: nothing is dropped.
+KINK_FULL = {"cfg4": 0.0, "cfg5": 0.75}
 
 
 @pytest.mark.parametrize("name", ["cfg4", "cfg5"])
 def test_full_width_parity(name):
-  out = parity.check_config(name, batch=192, check_grad=True, w_std=0.15)
+  out = parity.check_config(name, batch=192, check_grad=True, w_std=0.15, kink_max_frac=KINK_FULL[name])
   print(name, out)
 
 
-@pytest.mark.parametrize("name,batch", [("cfg4", 1 << 17), ("cfg5", 1 << 17)])
+@pytest.mark.parametrize("name", ["cfg4", "cfg5"])
+def test_full_width_parity_multi_chunk(name):
+  """What BASELINE's batch 2^20 executes and a one-chunk test never does: the per-op executor looping over chunks --
+  log-prob write-back at chunk offsets, gradient accumulation across chunks, a ragged last chunk.  Chunks of 128
+  samples turn batch 300 into 3 chunks (128 + 128 + 44) at a size the float64 oracle still finishes in seconds."""
+  with chunk_samples(128):
+    out = parity.check_config(name, batch=300, check_grad=True, w_std=0.15, kink_max_frac=KINK_FULL[name])
+  print(name, "3 chunks", out)
+
+
+@pytest.mark.parametrize("mode", ["layered"])
+@pytest.mark.parametrize("name", ["cfg4", "cfg5", "cfg2", "cond"])
+def test_scaled_configs_multi_chunk(name, mode):
+  with chunk_samples(128):
+    out = parity.check_config(name, batch=300, check_grad=True, mode=mode, **parity.SMALL.get(name, {}))
+  print(name, mode, "3 chunks", out)
+
+
+@pytest.mark.parametrize("name,batch", [("cfg4", (1 << 18) + 77), ("cfg5", (1 << 18) + 77)])
 def test_large_batch_properties(name, batch):
+  """Default chunk width (131072): batch 2^18 + 77 = two full chunks and a ragged third."""
   pm, pparams, om, oparams, y64, x64 = parity.build_pair(name, 8, 0, 0.15)
   dev = torch.device("cuda:0")
   params = parity.to_device(pparams, dev)
@@ -40,7 +66,7 @@ def test_large_batch_properties(name, batch):
   def loss(p, sl):
     return -torch.sum(pm.apply(p, None, method="log_prob", **kw(sl)))
 
-  half = batch // 2
+  half = batch // 2 + 5  # not a chunk boundary
   l_all, g_all = value_and_grad(lambda p: loss(p, slice(None)))(params)
   l_a, g_a = value_and_grad(lambda p: loss(p, slice(0, half)))(params)
   l_b, g_b = value_and_grad(lambda p: loss(p, slice(half, batch)))(params)

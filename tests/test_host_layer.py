@@ -134,6 +134,19 @@ def test_quirk_q1_bare_coupling_ignores_x():
   assert tuple(p["mlp/~/linear_0"]["w"].shape) == (4, 8)  # inside a Chain x is honoured (chain.py:36-41)
 
 
+def test_quirk_q1_is_one_sided_sampling_conditions_on_x():
+  # transformed_distribution.py:137: sample_and_log_prob always calls transform.forward_and_likelihood_contribution(z, x=x),
+  # so the SAME bare coupling that ignores x in log_prob (:87-88) does condition on x when sampling
+  def fn(method, **kw):
+    layer = sj.AffineMaskedCoupling(make_alternating_binary_mask(2), make_mlp([8, 8, 4]))
+    return sj.TransformedDistribution(_base(2), layer)(method=method, **kw)
+
+  p = hk.transform(fn).init(0, method="sample_and_log_prob", x=torch.zeros((10, 3)))
+  assert tuple(p["mlp/~/linear_0"]["w"].shape) == (2 + 3, 8)
+  traced, _ = hk.transform(fn).trace(method="sample_and_log_prob", x=torch.zeros((10, 3)))
+  assert traced[0].dim_x == 3
+
+
 def test_smoke_shapes_of_reference_tests_compile():
   """The constructor call patterns of the reference's smoke tests all trace and compile to a plan."""
   def rq_cond(d, k):
