@@ -7,6 +7,7 @@ timeout makes its peer raise instead of applying a stale gradient.  Needs 2 GPUs
 import json
 import os
 import socket
+import time
 
 import pytest
 import torch
@@ -30,7 +31,9 @@ def test_two_rank_train_step_matches_single_rank(tmp_path):
 
   out = str(tmp_path / "dp")
   ctx = mp.spawn(dp_worker.main, args=(2, _free_port(), out), nprocs=2, join=False)
-  ctx.join(timeout=600)
+  deadline = time.time() + 600
+  while not ctx.join(timeout=5):  # join() returns as soon as ONE process has exited: keep joining until all have
+    assert time.time() < deadline, "data-parallel workers did not finish"
   res = [json.load(open(f"{out}.{r}")) for r in range(2)]
   for r in res:
     for item in r["results"]:
