@@ -241,6 +241,10 @@ int64_t surj_profile_end(char* out, int64_t out_bytes);
  * time (rounded up to 128; default 131072, SURJ_B200_CHUNK at load time; 0 restores the default).  Returns the
  * previous value.  Changes surj_plan_workspace_bytes: query it again after setting. */
 int64_t surj_set_chunk_samples(int64_t samples);
+/* the fused conditioner + spline kernel of the per-op executor on (1, default; SURJ_B200_FUSION at load time) / off (0:
+ * every op is its own launch, theta goes through the workspace).  Returns the previous setting.  Changes
+ * surj_plan_workspace_bytes: query it again after setting. */
+int32_t surj_set_wide_fusion(int32_t on);
 
 const char* surj_last_error(void);
 int32_t surj_abi_version(void);

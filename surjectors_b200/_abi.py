@@ -124,6 +124,7 @@ _SIGNATURES = {
   "surj_profile_begin": (C.c_int, []),
   "surj_profile_end": (C.c_int64, [C.c_char_p, C.c_int64]),
   "surj_set_chunk_samples": (C.c_int64, [C.c_int64]),
+  "surj_set_wide_fusion": (C.c_int32, [C.c_int32]),
   "surj_last_error": (C.c_char_p, []),
   "surj_abi_version": (C.c_int32, []),
   "surj_registry_size": (C.c_int32, []),

@@ -21,12 +21,13 @@
 #include "vm_ops.cuh"
 #include "vm_plan.h"
 #include "vm_tc.cuh"
+#include "vm_fused.cuh"
 
 // ---- per-kernel timing (surj_profile_begin / surj_profile_end): every launch of the executor bracketed by events
 namespace prof {
-enum Kind { LINEAR_TC = 0, LINEAR_SIMT, DW_TC, DW_SIMT, ELEM, TILE, STAGE, N_KINDS };
+enum Kind { LINEAR_TC = 0, LINEAR_SIMT, DW_TC, DW_SIMT, ELEM, TILE, STAGE, FUSED_RQS, N_KINDS };
 const char* const kNames[N_KINDS] = {"linear_tcgen05", "linear_simt", "dw_tcgen05", "dw_simt", "per_sample_ops", "operand_tiling",
-                                     "staging_writeback"};
+                                     "staging_writeback", "fused_conditioner_spline_tcgen05"};
 struct Rec { int kind; double flops; cudaEvent_t a, b; };
 bool g_on = false;
 std::vector<Rec> g_recs;
@@ -289,6 +290,8 @@ inline size_t a256(size_t n) { return (n + 255) & ~(size_t)255; }
 // chunk width target: SURJ_B200_CHUNK at load time, surj_set_chunk_samples() afterwards (tests run multi-chunk cases
 // at oracle-sized batches with it; 0 restores the default)
 constexpr int64_t kDefaultChunk = 131072;
+// fused conditioner + spline kernel (vm_fused.cuh) on / off: SURJ_B200_FUSION at load time, surj_set_wide_fusion() afterwards
+std::atomic<int> g_fusion{[] { const char* e = getenv("SURJ_B200_FUSION"); return e ? atoi(e) : 1; }()};
 std::atomic<int64_t> g_chunk_target{[] { const char* e = getenv("SURJ_B200_CHUNK"); return e ? atoll(e) : kDefaultChunk; }()};
 inline int chunk_cols(int64_t B, int n_rows) {
   // rows of one chunk must stay within 8 GB; the target width trades L2 residency between kernels (small chunks)
@@ -305,23 +308,11 @@ inline bool tc_linear_op(const vm::Op& op) { return op.code == vm::OP_LINEAR && 
 // tensor-core bookkeeping of one program: tiled-weight offsets (deduplicated by matrix) and scratch sizes
 const VmTcInfo& tc_info(const VmPlan* v, int prog) {
   VmTcInfo& t = v->tc[prog];
-  if (t.ready) return t;
+  const int fusion_now = g_fusion.load(std::memory_order_relaxed);
+  if (t.ready && t.fusion_flag == fusion_now) return t;
+  t = VmTcInfo{};
+  t.fusion_flag = fusion_now;
   const std::vector<vm::Op>& ops = prog == VM_PROG_BWD ? v->ops_bwd : (prog == VM_PROG_GEN ? v->ops_gen : v->ops_fwd);
-  std::map<int, long long> seen;
-  t.w_off.assign(ops.size(), -1);
-  for (size_t i = 0; i < ops.size(); ++i) {
-    const vm::Op& op = ops[i];
-    if (!tc_linear_op(op)) continue;
-    const int n_in = op.a[1], n_real = op.a[12], tw = op.a[10];
-    const int nkb = (n_in + vmtc::PBK - 1) / vmtc::PBK;
-    auto it = seen.find(tw);
-    if (it == seen.end()) {
-      it = seen.emplace(tw, (long long)t.w_floats).first;
-      t.w_floats += (size_t)((n_real + vmtc::TM - 1) / vmtc::TM) * nkb * vmtc::BLOCK_FLOATS;
-    }
-    t.w_off[i] = it->second;
-    t.max_kpad = std::max(t.max_kpad, nkb * vmtc::PBK);
-  }
   // structural zeros at tile granularity, read off the gather table (masked weights are STAGE_ZERO)
   // structurally non-zero weights per matrix op (needed FLOPs per sample = 2 x this), read off the gather table
   t.nnz.assign(ops.size(), 0.0);
@@ -373,12 +364,90 @@ const VmTcInfo& tc_info(const VmPlan* v, int prog) {
       t.dw_skip[i] = skip;
     }
   }
+
+  // ---- fused conditioner + spline groups (vm_fused.cuh): LINEAR x (1..3 hidden + last), then RQS / RQS_BWD on the last
+  // layer's output, all widths multiples of 16 and <= 256
+  t.fused.clear();
+  t.fused_at.assign(ops.size(), -1);
+  t.img_mats.clear();
+  t.img_bytes = 0;
+  if (fusion_now) {
+    std::map<int, int> mat_of;  // wt_off -> img_mats index
+    for (size_t i = 0; i < ops.size(); ++i) {
+      if (ops[i].code != vm::OP_LINEAR) continue;
+      size_t e = i;
+      while (e < ops.size() && ops[e].code == vm::OP_LINEAR) ++e;
+      const int n_lin = (int)(e - i);
+      if (e >= ops.size() || n_lin < 2 || n_lin > vmf::MAX_HIDDEN + 1) { i = e - 1; continue; }
+      const vm::Op& sp = ops[e];
+      const bool is_fwd = sp.code == vm::OP_RQS, is_bwd = sp.code == vm::OP_RQS_BWD;
+      if (!is_fwd && !is_bwd) { i = e - 1; continue; }
+      const int n_t = is_fwd ? sp.a[2] : sp.a[1], th = is_fwd ? sp.a[4] : sp.a[3], Kb = is_fwd ? sp.a[5] : sp.a[4];
+      const int Pp = 3 * Kb + 1;
+      bool ok = Kb >= 1 && 3 * Kb + 16 <= vmf::NMAX && n_t >= 1;
+      for (int l = 0; l < n_lin && ok; ++l) {
+        const vm::Op& o = ops[i + l];
+        const bool last = l == n_lin - 1;
+        ok = ok && o.a[8] == 0 && o.a[1] >= 1 && o.a[1] <= vmf::KMAX;
+        if (l > 0) ok = ok && o.a[0] == ops[i + l - 1].a[4] && o.a[1] == ops[i + l - 1].a[12];
+        if (!last) ok = ok && o.a[12] % 16 == 0 && o.a[12] >= 16 && o.a[12] <= vmf::NMAX && o.a[5] == o.a[12];
+        else ok = ok && o.a[4] == th && o.a[12] == n_t * Pp && o.a[7] == vm::ACT_IDENTITY && o.a[9] < 0;
+      }
+      if (!ok) { i = e - 1; continue; }
+      VmFusedGroup g;
+      g.first = (int)i; g.last = (int)e;
+      for (int l = 0; l < n_lin; ++l) {
+        const vm::Op& o = ops[i + l];
+        const bool last = l == n_lin - 1;
+        auto it = mat_of.find(o.a[10]);
+        if (it == mat_of.end()) {
+          VmImgMat m{};
+          m.wt_off = o.a[10]; m.ldt = o.a[11]; m.n_rows = o.a[12]; m.n_k = o.a[1];
+          m.rows_per_block = last ? Pp : o.a[12];
+          m.n_blocks = last ? n_t : 1;
+          m.N = last ? (Pp + 15) / 16 * 16 : o.a[12];
+          m.k_pad = (o.a[1] + 15) / 16 * 16;
+          m.scale_slot = (int)t.img_mats.size();
+          m.img_off = (long long)t.img_bytes;
+          t.img_bytes += (size_t)m.n_blocks * (m.k_pad / vmf::KS) * ((size_t)m.N * 64);
+          t.img_bytes = (t.img_bytes + 255) & ~(size_t)255;
+          it = mat_of.emplace(o.a[10], (int)t.img_mats.size()).first;
+          t.img_mats.push_back(m);
+        }
+        g.mats[l] = it->second;
+        g.nnz += t.nnz[i + l];
+      }
+      t.fused_at[i] = (int)t.fused.size();
+      t.fused.push_back(g);
+      i = e;
+    }
+  }
+  std::vector<char> in_group(ops.size(), 0);
+  for (const VmFusedGroup& g : t.fused)
+    for (int q = g.first; q <= g.last; ++q) in_group[q] = 1;
+  std::map<int, long long> seen;
+  t.w_off.assign(ops.size(), -1);
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const vm::Op& op = ops[i];
+    if (!tc_linear_op(op) || in_group[i]) continue;
+    const int n_in = op.a[1], n_real = op.a[12], tw = op.a[10];
+    const int nkb = (n_in + vmtc::PBK - 1) / vmtc::PBK;
+    auto it = seen.find(tw);
+    if (it == seen.end()) {
+      it = seen.emplace(tw, (long long)t.w_floats).first;
+      t.w_floats += (size_t)((n_real + vmtc::TM - 1) / vmtc::TM) * nkb * vmtc::BLOCK_FLOATS;
+    }
+    t.w_off[i] = it->second;
+    t.max_kpad = std::max(t.max_kpad, nkb * vmtc::PBK);
+  }
   t.ready = true;
   return t;
 }
 
 struct Carve {
   float *par, *grad, *scal, *scal_g, *loss, *rows, *w_tiles, *a_tiles;
+  unsigned char* img;   // fp16 hi / lo weight images of the fused groups
+  unsigned* scales;     // max |w| per image matrix (float bits)
   size_t total;
 };
 Carve carve(const VmPlan* v, void* ws, int C, int prog) {
@@ -396,10 +465,18 @@ Carve carve(const VmPlan* v, void* ws, int C, int prog) {
   const VmTcInfo& t = tc_info(v, prog);
   k.w_tiles = take(pipe_mode ? std::max<size_t>(t.w_floats, 1) : 1);
   k.a_tiles = take(pipe_mode ? std::max<size_t>((size_t)t.max_kpad * 2 * C, 1) : 1);
+  k.img = (unsigned char*)take(std::max<size_t>(t.img_bytes / 4, 1));
+  k.scales = (unsigned*)take(std::max<size_t>(t.img_mats.size(), 1));
   k.total = o;
   return k;
 }
 }  // namespace
+
+extern "C" int32_t surj_set_wide_fusion(int32_t on) {
+  const int prev = g_fusion.load();
+  g_fusion.store(on ? 1 : 0);
+  return prev;
+}
 
 extern "C" int64_t surj_set_chunk_samples(int64_t samples) {
   const int64_t prev = g_chunk_target.load();
@@ -417,9 +494,12 @@ size_t vm_global_workspace_bytes(const VmPlan* v, int64_t B, bool backward) {
 
 int vm_global_launches(const VmPlan* v, int64_t B, bool backward) {
   const std::vector<vm::Op>& ops = backward ? v->ops_bwd : v->ops_fwd;
+  const VmTcInfo& tci = tc_info(v, backward ? VM_PROG_BWD : VM_PROG_FWD);
   int per_chunk = 0;
   bool in_run = false;
-  for (const vm::Op& op : ops) {
+  for (size_t pc = 0; pc < ops.size(); ++pc) {
+    if (tci.fused_at[pc] >= 0) { ++per_chunk; in_run = false; pc = (size_t)tci.fused[tci.fused_at[pc]].last; continue; }
+    const vm::Op& op = ops[pc];
     const bool mat = op.code == vm::OP_LINEAR || op.code == vm::OP_LINEAR_DW;
     if (mat) { ++per_chunk; in_run = false; }
     else if (!in_run) { ++per_chunk; in_run = true; }
@@ -491,12 +571,67 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
                                                  (op.a[1] + vmtc::PBK - 1) / vmtc::PBK, k.w_tiles + tci.w_off[i]);
     }
   }
+  // fused conditioner + spline groups: max |w| per matrix, then the fp16 hi / lo images in ring order, once per call
+  if (!tci.img_mats.empty()) {
+    static const bool attr = [] {
+      cudaFuncSetAttribute(vmf::vg_fused_rqs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmf::SMEM_BYTES);
+      return true;
+    }();
+    (void)attr;
+    prof::Scope ps(st, prof::TILE, 0.0);
+    cudaMemsetAsync(k.scales, 0, tci.img_mats.size() * sizeof(unsigned), st);
+    for (size_t m0 = 0; m0 < tci.img_mats.size(); m0 += vmf::IMG_BATCH) {
+      vmf::ImgBatch bt;
+      const int nb = (int)std::min<size_t>(vmf::IMG_BATCH, tci.img_mats.size() - m0);
+      for (int q = 0; q < nb; ++q) {
+        const VmImgMat& a = tci.img_mats[m0 + q];
+        bt.m[q] = vmf::ImgMat{a.wt_off, a.ldt, a.n_rows, a.n_k, a.rows_per_block, a.n_blocks, a.N, a.k_pad, a.scale_slot, a.img_off};
+      }
+      vmf::vf_wmax<<<dim3(64, nb), 256, 0, st>>>(k.par, bt, k.scales);
+      vmf::vf_image<<<dim3(128, nb), 256, 0, st>>>(k.par, bt, k.scales, k.img);
+    }
+  }
   for (int64_t base = 0; base < B; base += C) {
     const int cols = (int)std::min<int64_t>(C, (B - base + 127) / 128 * 128);  // columns in use (multiple of 128)
     size_t pc = 0;
     bool first = true;
     while (pc < ops.size()) {
       const vm::Op& op = ops[pc];
+      if (tci.fused_at[pc] >= 0) {  // conditioner MLP + spline (or its VJP) of one coupling layer in ONE launch
+        const VmFusedGroup& g = tci.fused[tci.fused_at[pc]];
+        const vm::Op& sp = ops[g.last];
+        const int n_lin = g.last - g.first;
+        vmf::Desc d{};
+        d.in_row = op.a[0]; d.n_in = op.a[1];
+        d.n_hidden = n_lin - 1;
+        d.mode = sp.code == vm::OP_RQS_BWD ? 1 : 0;
+        for (int l = 0; l < n_lin; ++l) {
+          const vm::Op& o = ops[g.first + l];
+          const VmImgMat& im = tci.img_mats[g.mats[l]];
+          d.k_pad[l] = im.k_pad; d.img_off[l] = im.img_off; d.scale_slot[l] = im.scale_slot;
+          if (l < n_lin - 1) {
+            d.h_n[l] = o.a[12]; d.h_boff[l] = o.a[6]; d.h_act[l] = o.a[7];
+            d.h_post[l] = d.mode ? o.a[4] : -1;
+            d.h_pre[l] = d.mode ? o.a[9] : -1;
+          } else {
+            d.b_off = o.a[6]; d.N = im.N; d.P = im.rows_per_block; d.n_t = im.n_blocks;
+          }
+        }
+        if (d.mode == 0) {
+          d.ein_row = sp.a[0]; d.eout_row = sp.a[1]; d.tdims = sp.a[3]; d.th_row = sp.a[4]; d.K_bins = sp.a[5]; d.inner = sp.a[6];
+          d.skip_lp = sp.a[7];
+        } else {
+          d.ein_row = sp.a[0]; d.tdims = sp.a[2]; d.th_row = sp.a[3]; d.K_bins = sp.a[4]; d.inner = sp.a[5];
+          d.gout_row = sp.a[6]; d.gin_row = sp.a[7];
+        }
+        d.lo = sp.f0; d.hi = sp.f1;
+        const int n_tiles = cols / vmf::TM;
+        prof::Scope ps(st, prof::FUSED_RQS, 2.0 * g.nnz * (double)cols);
+        vmf::vg_fused_rqs<<<std::min(n_tiles, v->n_sm), vmf::THREADS, vmf::SMEM_BYTES, st>>>(d, k.rows, C, n_tiles, k.par, P.itab, k.img,
+                                                                                            k.scales);
+        pc = (size_t)g.last + 1;
+        continue;
+      }
       if (op.code == vm::OP_LINEAR) {
         const double fl = 2.0 * tci.nnz[pc] * (double)cols;
         if (pipe && tci.w_off[pc] >= 0) {  // tcgen05 3xTF32, TMA-fed pipeline on pre-tiled operands

@@ -14,8 +14,23 @@ struct VmKRange {
   unsigned short lo[8], hi[8];
   int enabled;
 };
+// One fused conditioner + spline group of a program (vm_fused.cuh): ops [first, last] = LINEAR x (n_hidden + 1), RQS / RQS_BWD
+struct VmFusedGroup {
+  int first = 0, last = 0;       // op indices (inclusive)
+  int mats[4] = {-1, -1, -1, -1}; // index into VmTcInfo::img_mats of every matrix
+  double nnz = 0.0;              // structurally non-zero weights of its matrices (needed FLOPs per sample = 2 x this)
+};
+struct VmImgMat {  // mirrors vmf::ImgMat (kept POD here so that this header stays CUDA-free)
+  int wt_off, ldt, n_rows, n_k, rows_per_block, n_blocks, N, k_pad, scale_slot;
+  long long img_off;
+};
 struct VmTcInfo {
   bool ready = false;
+  int fusion_flag = -1;                    // the fusion setting `fused` was computed under
+  std::vector<VmFusedGroup> fused;         // fused conditioner + spline groups, by first op
+  std::vector<int> fused_at;               // per op: index into `fused` if a group starts there, else -1
+  std::vector<VmImgMat> img_mats;          // weight images of the fused groups (deduplicated by matrix)
+  size_t img_bytes = 0;
   std::vector<VmKRange> kr;                // per op (LINEAR on the pipelined kernel)
   std::vector<unsigned long long> dw_skip; // per op (LINEAR_DW): bit (i_tile * n_j_tiles + j_tile) set = all-zero tile
   std::vector<double> nnz;                 // per op (LINEAR / LINEAR_DW): structurally non-zero weights of its matrix
