@@ -44,7 +44,19 @@ struct Scope {
 };
 }  // namespace prof
 
+// SURJ_B200_FUSED_DBG=1: wait-cycle counters of the fused conditioner + spline kernel (CTA 0), printed by surj_profile_end
+static long long* fused_dbg_buffer() {
+  static long long* buf = [] {
+    long long* p = nullptr;
+    const char* e = getenv("SURJ_B200_FUSED_DBG");
+    if (e && atoi(e)) { cudaMalloc(&p, 16 * sizeof(long long)); cudaMemset(p, 0, 16 * sizeof(long long)); }
+    return p;
+  }();
+  return buf;
+}
+
 extern "C" int surj_profile_begin(void) {
+  if (long long* d = fused_dbg_buffer()) cudaMemset(d, 0, 16 * sizeof(long long));
   for (auto& r : prof::g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   prof::g_recs.clear();
   prof::g_on = true;
@@ -54,6 +66,12 @@ extern "C" int64_t surj_profile_end(char* out, int64_t out_bytes) {
   if (!prof::g_on) return 0;
   prof::g_on = false;
   cudaDeviceSynchronize();
+  if (long long* d = fused_dbg_buffer()) {
+    long long h[16];
+    cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[fused dbg, CTA 0, cycles] producer waits free slot %lld | MMA waits weights %lld, accumulator %lld, operand %lld | "
+            "epilogue warp 2: waits accumulator %lld, hidden phases %lld, bias staging %lld, input load %lld, spline %lld | CTA total %lld\n", h[0], h[1], h[2], h[3], h[4], h[6], h[7], h[9], h[8], h[5]);
+  }
   double ms[prof::N_KINDS] = {0}, fl[prof::N_KINDS] = {0};
   long long n[prof::N_KINDS] = {0};
   for (auto& r : prof::g_recs) {
@@ -574,7 +592,8 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   // fused conditioner + spline groups: max |w| per matrix, then the fp16 hi / lo images in ring order, once per call
   if (!tci.img_mats.empty()) {
     static const bool attr = [] {
-      cudaFuncSetAttribute(vmf::vg_fused_rqs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmf::SMEM_BYTES);
+      cudaFuncSetAttribute(vmf::vg_fused_rqs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmf::SMEM_BYTES);
+      cudaFuncSetAttribute(vmf::vg_fused_rqs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmf::SMEM_BYTES);
       return true;
     }();
     (void)attr;
@@ -627,8 +646,10 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
         d.lo = sp.f0; d.hi = sp.f1;
         const int n_tiles = cols / vmf::TM;
         prof::Scope ps(st, prof::FUSED_RQS, 2.0 * g.nnz * (double)cols);
-        vmf::vg_fused_rqs<<<std::min(n_tiles, v->n_sm), vmf::THREADS, vmf::SMEM_BYTES, st>>>(d, k.rows, C, n_tiles, k.par, P.itab, k.img,
-                                                                                            k.scales);
+        const int grid = std::min(n_tiles, v->n_sm);
+        long long* dbg = fused_dbg_buffer();
+        if (d.mode) vmf::vg_fused_rqs<1><<<grid, vmf::THREADS, vmf::SMEM_BYTES, st>>>(d, k.rows, C, n_tiles, k.par, P.itab, k.img, k.scales, dbg);
+        else vmf::vg_fused_rqs<0><<<grid, vmf::THREADS, vmf::SMEM_BYTES, st>>>(d, k.rows, C, n_tiles, k.par, P.itab, k.img, k.scales, dbg);
         pc = (size_t)g.last + 1;
         continue;
       }

@@ -409,7 +409,9 @@ VmPlan* vm_compile(const SurjPlan* plan, std::string* why) {
             if (dxu) C.dec.push_back(mk(vm::OP_ADD, {GX, c_row + K, dxu}));
             B.scratch_reset();  // the decoder is done: the conditioner reuses its rows
           } else {
-            C.bwd.push_back(mk(vm::OP_COPY, {Gin, Gout, D}));
+            // (emitted ahead of the training-mode recompute, not between it and the inner bijector's VJP: the per-op
+            // executor fuses [conditioner products, spline VJP] into one launch when they are adjacent)
+            C.dec.push_back(mk(vm::OP_COPY, {Gin, Gout, D}));
           }
           emit_fwd(C.train, true, rows, m_row);
           const int th = rows.back().post_row;

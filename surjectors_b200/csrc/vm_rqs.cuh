@@ -296,138 +296,5 @@ VM_DEV float rqs_bwd(Th& th, int K, float lo, float hi, float v, bool forward, f
   return G.g_v;
 }
 
-// ---- the same spline driven by a CHUNK source: src.load(col, v) yields theta[col .. col + 15] (entries past 3K are
-// unspecified).  Used where theta sits in tensor memory (vm_fused.cuh) and can only be read in warp-uniform column
-// ranges.  The arithmetic and its order are those of rqs_locate / rqs_bwd above, value for value.
-constexpr int RQS_CH = 16;
-
-template <class Src>
-VM_DEV void rqs_locate_chunked(const Src& src, int K, float lo, float hi, float v, bool forward, RqsBin& b) {
-  float mw = -INFINITY, mh = -INFINITY;
-  for (int k0 = 0; k0 < K; k0 += RQS_CH) {
-    float w[RQS_CH], h[RQS_CH];
-    src.load2(k0, w, K + k0, h);
-#pragma unroll
-    for (int i = 0; i < RQS_CH; ++i)
-      if (k0 + i < K) { mw = fmaxf(mw, w[i]); mh = fmaxf(mh, h[i]); }
-  }
-  float zw = 0.0f, zh = 0.0f;
-  for (int k0 = 0; k0 < K; k0 += RQS_CH) {
-    float w[RQS_CH], h[RQS_CH];
-    src.load2(k0, w, K + k0, h);
-#pragma unroll
-    for (int i = 0; i < RQS_CH; ++i)
-      if (k0 + i < K) { zw += expf(w[i] - mw); zh += expf(h[i] - mh); }
-  }
-  b.mw = mw; b.mh = mh; b.zw = zw; b.zh = zh;
-  b.pw_cum = b.pw_bin = b.ph_cum = b.ph_bin = 0.0f;
-  const bool below = v <= lo, above = !below && v >= hi;
-  const float span = (hi - lo) - (float)K * VM_RQS_MIN_BIN;
-  const float iw = 1.0f / zw, ih = 1.0f / zh;
-  float xk = lo, yk = lo, cw = 0.0f, ch = 0.0f, ew = 0.0f, eh = 0.0f, cpw = 0.0f, cph = 0.0f;
-  int bin = -2;
-  b.x0 = b.x1 = b.y0 = b.y1 = below ? lo : hi;
-  b.bw = b.bh = 1.0f;
-  // the walk is warp-uniform (tensor-memory loads are warp-collective); lanes in a tail simply ignore its result
-  for (int k0 = 0; k0 < K; k0 += RQS_CH) {
-    float w[RQS_CH], h[RQS_CH];
-    src.load2(k0, w, K + k0, h);
-#pragma unroll
-    for (int i = 0; i < RQS_CH; ++i) {
-      const int k = k0 + i;
-      if (k < K && !below && !above) {
-        const float pw = expf(w[i] - mw) * iw, ph = expf(h[i] - mh) * ih;
-        const float wk = pw * span + VM_RQS_MIN_BIN, hk = ph * span + VM_RQS_MIN_BIN;
-        {
-          const float yv = wk - ew, t = cw + yv;
-          ew = (t - cw) - yv;
-          cw = t;
-        }
-        {
-          const float yv = hk - eh, t = ch + yv;
-          eh = (t - ch) - yv;
-          ch = t;
-        }
-        const float xn = (k == K - 1) ? hi : lo + cw;
-        const float yn = (k == K - 1) ? hi : lo + ch;
-        const float p0 = forward ? xk : yk, p1 = forward ? xn : yn;
-        if (bin == -2 && ((v >= p0 && v < p1) || (k == 0 && !(v == v)))) {
-          bin = k;
-          b.x0 = xk; b.x1 = xn; b.y0 = yk; b.y1 = yn;
-          b.bw = (k == K - 1) ? hi - xk : wk;
-          b.bh = (k == K - 1) ? hi - yk : hk;
-          b.pw_cum = cpw; b.pw_bin = pw; b.ph_cum = cph; b.ph_bin = ph;
-        }
-        if (k == 0 && bin == -2) {
-          b.x0 = xk; b.x1 = xn; b.y0 = yk; b.y1 = yn;
-          b.bw = (K == 1) ? hi - xk : wk;
-          b.bh = (K == 1) ? hi - yk : hk;
-          b.pw_bin = pw; b.ph_bin = ph;
-        }
-        xk = xn; yk = yn; cpw += pw; cph += ph;
-      }
-    }
-  }
-  if (below) bin = -1;
-  else if (above) bin = K;
-  else if (bin == -2) bin = 0;
-  b.bin = bin;
-  // the two slope parameters: a predicated sweep over the K + 1 of them (a lane cannot address tensor memory by its own bin)
-  const int s0 = bin < 0 ? 0 : (bin >= K ? K : bin), s1 = (bin < 0 || bin >= K) ? s0 : bin + 1;
-  float u0 = 0.0f, u1 = 0.0f;
-  for (int k0 = 0; k0 <= K; k0 += RQS_CH) {
-    float u[RQS_CH];
-    src.load(2 * K + k0, u);
-#pragma unroll
-    for (int i = 0; i < RQS_CH; ++i) {
-      if (k0 + i == s0) u0 = u[i];
-      if (k0 + i == s1) u1 = u[i];
-    }
-  }
-  b.u0 = u0; b.u1 = u1;
-  b.d0 = rqs_slope(u0);
-  b.d1 = rqs_slope(u1);
-}
-
-// VJP over chunks: theta from src, its cotangent to sink.store(col, g, n_valid) (g_theta[col .. col + n_valid)).
-template <class Src, class Sink>
-VM_DEV float rqs_bwd_chunked(const Src& src, Sink& sink, int K, float lo, float hi, float v, bool forward, float g_out, float g_ld) {
-  RqsBin b;
-  rqs_locate_chunked(src, K, lo, hi, v, forward, b);
-  RqsGrad G;
-  rqs_bwd_core(b, K, lo, hi, v, forward, g_out, g_ld, G);
-  const bool tail = G.ks >= 0;
-  const int kb = b.bin;
-  const float span = (hi - lo) - (float)K * VM_RQS_MIN_BIN;
-  const float iw = 1.0f / b.zw, ih = 1.0f / b.zh;
-  for (int k0 = 0; k0 < K; k0 += RQS_CH) {
-    float w[RQS_CH], h[RQS_CH];
-    src.load2(k0, w, K + k0, h);
-#pragma unroll
-    for (int i = 0; i < RQS_CH; ++i) {
-      const int k = k0 + i;
-      const float pw = expf(w[i] - b.mw) * iw, ph = expf(h[i] - b.mh) * ih;
-      const float sw = k < kb ? G.Aw : (k == kb ? G.Bw : 0.0f), sh = k < kb ? G.Ah : (k == kb ? G.Bh : 0.0f);
-      w[i] = tail ? 0.0f : span * pw * (sw - G.dotw);
-      h[i] = tail ? 0.0f : span * ph * (sh - G.doth);
-    }
-    const int nv = min(RQS_CH, K - k0);
-    sink.store(k0, w, nv);
-    sink.store(K + k0, h, nv);
-  }
-  for (int k0 = 0; k0 <= K; k0 += RQS_CH) {
-    float u[RQS_CH];
-#pragma unroll
-    for (int i = 0; i < RQS_CH; ++i) {
-      const int k = k0 + i;
-      float g = 0.0f;
-      if (tail) { if (2 * K + k == G.ks) g = G.g_tail; }
-      else { if (k == kb) g = G.g_u0; if (k == kb + 1) g = G.g_u1; }
-      u[i] = g;
-    }
-    sink.store(2 * K + k0, u, min(RQS_CH, K + 1 - k0));
-  }
-  return G.g_v;
-}
 
 }  // namespace vm
