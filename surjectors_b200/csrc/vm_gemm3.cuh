@@ -1,0 +1,371 @@
+// FP32-grade tcgen05 matrix products of the per-op executor, second generation (sm_100a): the products the fused
+// conditioner + spline kernel (vm_fused.cuh) leaves over -- the weight-gradient contractions and input-gradient products
+// of the backward pass, decoders, MADE layers:
+//
+//   LINEAR     out[j][s] = act(b[j] (+ prev) + sum_i Wt[j][i] in[i][s])    M = 128 samples, N <= 256 outputs, K = inputs
+//              (hk.Linear / MaskedLinear, conditioners/mlp.py:24-29, nn/masked_linear.py:35-58; with the transposed copy
+//              of W it is the input-gradient product g W^T of SURVEY appendix C)
+//   LINEAR_DW  grad[i][j] += sum_s in[i][s] g[j][s], grad[b][j] += sum_s g[j][s]  M = 128 inputs, N <= 256 outputs, K = samples
+//
+// Both read their operands as plain float32 straight from where they live -- rows [row][sample] of the workspace and
+// the staged parameters -- with cp.async into a shared-memory ring in the K-major no-swizzle UMMA layout (LINEAR's
+// activation operand is sample-major in memory: it is transposed on the fly by 4-byte cp.async, so no separate
+// re-tiling pass and no second copy of the activations exist).  The thread that loaded a 16-byte piece also splits it:
+// the tensor core reads the float32 bits as TF32 (it ignores the 13 low mantissa bits: hi = truncation, free) and the
+// thread writes lo = x - trunc(x) to a second ring; per 8-wide k step the issuing thread runs lo*hi + hi*lo + hi*hi
+// (3xTF32, product error 2^-21).  The tensor core's accumulator add truncates, so only BLK = 256 k are accumulated
+// inside it; four drain warps add every finished block into a MASTER accumulator in tensor memory with round-to-nearest
+// adds (tcgen05.ld / FADD / tcgen05.st) -- N = 256 is the MMA shape that reaches the tensor pipe's rate (a 128-wide
+// MMA costs the same 140-cycle floor, tools/ubench/f16_probe.cu), and 2 x 256 columns are all of tensor memory.
+// Warp roles (416 threads): 0..7 load + split, 8 issues the MMAs, 9..12 drain / epilogue (TMEM lanes 32 * (warp % 4)).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vm.cuh"
+#include "vm_plan.h"
+#include "vm_tc.cuh"
+
+namespace vmg {
+
+using vmtc::fence_async_smem;
+using vmtc::mbar_arrive;
+using vmtc::mbar_init;
+using vmtc::mbar_wait;
+using vmtc::smem_u32;
+using vmtc::tc_fence_after;
+using vmtc::tc_fence_before;
+using vmtc::umma_commit;
+
+constexpr int TM = 128, TN = 256, KS = 16;     // tile, k per stage
+constexpr int BLK = 16;                        // stages per accumulation block inside the tensor core (256 k)
+constexpr int RS = 4, LS = 3;                  // raw / lo ring depths
+constexpr int A_BYTES = TM * KS * 4, B_BYTES = TN * KS * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int LOADERS = 256, THREADS = 416;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)(RS + LS) * STAGE_BYTES + 256;
+
+__device__ __forceinline__ uint32_t soff(int r, int k) {  // byte offset of element (r, k) in a [rows x 16] K-major tile
+  return (uint32_t)((r >> 3) * 512 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
+}
+__device__ __forceinline__ uint64_t desc16(uint32_t saddr) {  // LBO 128 B, SBO 512 B (4 core matrices of 4 k per 8-row group)
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | (32ull << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp4(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tm_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tm_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tm_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct Args {
+  // operands
+  const float* a_base; long long a_pitch; int a_rows;  // LINEAR: in rows [k][sample] (+ sample offset), a_rows = K;  DW: in rows [i][sample], a_rows = valid i
+  const float* b_base; long long b_pitch; int b_rows;  // B[n][k]: LINEAR: Wt rows (K-major); DW: g rows [j][sample]; b_rows = valid n of this tile set
+  int K;                                               // LINEAR: n_in; DW: samples of the slab set (per CTA: [k_begin, k_end))
+  int k_slab;                                          // DW: samples per CTA (multiple of 16); LINEAR: unused
+  // LINEAR epilogue
+  float* rows; long long C;                            // row workspace
+  int out_row, pre_row, n_out, b_off, act, accumulate; // n_out: padded outputs written
+  const float* par;
+  // DW epilogue
+  float* grad; int w_off, ld, gb_off, n_in;            // grad[w_off + i * ld + j], grad[gb_off + j]
+  VmKRange kr;                                         // LINEAR: k-stage range per 128-output tile (structural zeros), by value
+  unsigned long long skip;                             // DW: all-zero 128 x 128 tiles (bit i_tile * n_j128 + j128_tile)
+  int n_j128;
+};
+
+// MODE 0: LINEAR, grid (sample tiles, ceil(n_out / 256)).   MODE 1: LINEAR_DW, grid (ceil(n_in / 128), ceil(n_out / 256), slabs).
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+vg_gemm3(const __grid_constant__ Args g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* raw = base;                                  // [RS][A | B]
+  unsigned char* lo = base + (size_t)RS * STAGE_BYTES;        // [LS][A | B]
+  uint64_t* bars = (uint64_t*)(lo + (size_t)LS * STAGE_BYTES);
+  uint64_t* full = bars;             // [LS]  256 arrivals: stage split and visible
+  uint64_t* lo_empty = full + LS;    // [LS]  MMA commit
+  uint64_t* raw_empty = lo_empty + LS;  // [RS] MMA commit
+  uint64_t* blk_full = raw_empty + RS;  // [1]  MMA commit: a block's accumulator is complete
+  uint64_t* blk_done = blk_full + 1;    // [1]  4 arrivals: the block has been added to the master
+  uint32_t* tmem_slot = (uint32_t*)(blk_done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- this CTA's problem
+  const int n0 = blockIdx.y * TN;                        // first output (B row) of the tile
+  const int n_valid = min(TN, g.b_rows - n0);            // B rows that exist
+  const int n_tile = (max(n_valid, 16) + 15) & ~15;      // MMA N
+  int m0 = 0, k_begin = 0, k_end = g.K;
+  if (MODE == 0) {
+    m0 = blockIdx.x * TM;                                // first sample of the tile
+    if (g.kr.enabled) {  // structural zeros: k stages that can contribute, per 128 outputs -> union over this tile's two halves
+      int l = 1 << 30, h = 0;
+      for (int half = 0; half < 2; ++half) {
+        const int tl = 2 * (int)blockIdx.y + half;
+        if (tl < 8 && half * 128 < n_valid && g.kr.hi[tl] > g.kr.lo[tl]) { l = min(l, (int)g.kr.lo[tl]); h = max(h, (int)g.kr.hi[tl]); }
+      }
+      k_begin = h > 0 ? l * KS : 0;
+      k_end = h > 0 ? min(g.K, h * KS) : 0;
+    }
+  } else {
+    m0 = blockIdx.x * TM;                                // first input feature of the tile
+    k_begin = blockIdx.z * g.k_slab; k_end = min(g.K, k_begin + g.k_slab);
+  }
+  const int m_valid = MODE == 0 ? TM : min(TM, g.a_rows - m0);
+  const int n_stages = k_end > k_begin ? (k_end - k_begin + KS - 1) / KS : 0;
+  const int n_blocks = (n_stages + BLK - 1) / BLK;
+  bool skip_tile = false;
+  if (MODE == 1 && g.skip != 0ull) {  // both 128-column halves structurally zero: nothing but the bias gradient to do
+    const int j128 = 2 * blockIdx.y;
+    const bool z0 = (g.skip >> (blockIdx.x * g.n_j128 + j128)) & 1ull;
+    const bool z1 = (j128 + 1 >= g.n_j128) || ((g.skip >> (blockIdx.x * g.n_j128 + j128 + 1)) & 1ull);
+    skip_tile = z0 && z1;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < LS; ++s) { mbar_init(full + s, LOADERS); mbar_init(lo_empty + s, 1); }
+    for (int s = 0; s < RS; ++s) mbar_init(raw_empty + s, 1);
+    mbar_init(blk_full, 1);
+    mbar_init(blk_done, 4);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_work = tmem, t_master = tmem + TN;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ loaders: cp.async, then split what they loaded
+    // A tile 128 x 16 floats = 512 pieces of 16 B (2 per thread); B tile 256 x 16 = 1024 pieces (4 per thread);
+    // piece q -> row q / 4, k quarter q % 4 (K-major sources).  LINEAR's A is sample-major: element-wise 4-byte copies,
+    // thread -> sample tid % 128, k quarters tid / 128 and tid / 128 + 2.
+    // (Measured alternative: two sets of four warps taking the stages in turn, each with two stage times for its
+    // landed -> split -> fence -> arrive -> refill chain, but only one stage in flight per set: 286 vs 209 ms for the
+    // weight-gradient products of a cfg4 train step -- bytes in flight matter more than the chain's latency.)
+    float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // DW: running sums of this thread's four g rows (bias gradient)
+    auto issue = [&](int t) {
+      const int k0 = k_begin + t * KS;
+      const uint32_t sa = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sb = sa + A_BYTES;
+      if (MODE == 0) {
+        const int s = tid & 127;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int kq = (tid >> 7) + 2 * e;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = 4 * kq + i;
+            const bool ok = k0 + k < k_end;
+            cp4(sa + soff(s, k), g.a_base + (long long)(ok ? k0 + k : 0) * g.a_pitch + m0 + s, ok ? 4 : 0);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int q = tid + LOADERS * e, r = q >> 2, kq = q & 3;
+          const int kk = k0 + 4 * kq;
+          const int nb = (r < m_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
+          cp16(sa + soff(r, 4 * kq), g.a_base + (long long)(nb ? m0 + r : 0) * g.a_pitch + (nb ? kk : 0), nb);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q = tid + LOADERS * e, r = q >> 2, kq = q & 3;
+        const int kk = k0 + 4 * kq;
+        const int nb = (r < n_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
+        if (r < n_tile) cp16(sb + soff(r, 4 * kq), g.b_base + (long long)(nb ? n0 + r : 0) * g.b_pitch + (nb ? kk : 0), nb);
+      }
+    };
+    auto split = [&](int t) {
+      unsigned char* sr = raw + (size_t)(t % RS) * STAGE_BYTES;
+      unsigned char* sl = lo + (size_t)(t % LS) * STAGE_BYTES;
+      auto one = [&](uint32_t off, float* sum) {
+        const float4 x = *reinterpret_cast<const float4*>(sr + off);
+        float4 l;
+        l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+        l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+        l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+        l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+        *reinterpret_cast<float4*>(sl + off) = l;
+        if (sum != nullptr) *sum += (x.x + x.y) + (x.z + x.w);
+      };
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) one(soff(tid & 127, 4 * ((tid >> 7) + 2 * e)), nullptr);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int q = tid + LOADERS * e;
+          one(soff(q >> 2, 4 * (q & 3)), nullptr);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q = tid + LOADERS * e, r = q >> 2;
+        if (r < n_tile) one(A_BYTES + soff(r, 4 * (q & 3)), MODE == 1 ? &bsum[e] : nullptr);
+      }
+    };
+    if (!skip_tile) {
+      // RS - 1 stages in flight.  The refill of a slot is issued at the END of an iteration (it waits for the MMAs of the
+      // previous stage, which have had a whole split to finish), so splitting stage t + 1 overlaps the MMAs of stage t.
+      for (int t = 0; t < RS - 1; ++t) {
+        if (t < n_stages) issue(t);
+        cp_commit();
+      }
+      for (int t = 0; t < n_stages; ++t) {
+        cp_wait<RS - 2>();                                   // this thread's pieces of stage t have landed
+        if (t >= LS) mbar_wait(lo_empty + t % LS, (uint32_t)(t / LS - 1) & 1u);
+        split(t);
+        fence_async_smem();
+        mbar_arrive(full + t % LS);
+        const int tn = t + RS - 1;                           // refill the slot stage t - 1 used
+        if (tn < n_stages) {
+          if (tn >= RS) mbar_wait(raw_empty + tn % RS, (uint32_t)(tn / RS - 1) & 1u);
+          issue(tn);
+        }
+        cp_commit();
+      }
+    } else if (MODE == 1 && blockIdx.x == 0 && g.gb_off >= 0) {
+      // masked tile that still owes the bias gradient of its columns: plain column sums
+      for (int j = warp; j < n_valid; j += 8) {
+        const float* gr = g.b_base + (long long)(n0 + j) * g.b_pitch;
+        float a = 0.0f;
+        for (int s = k_begin + lane; s < k_end; s += 32) a += gr[s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) atomicAdd(g.grad + g.gb_off + n0 + j, a);
+      }
+    }
+    if (MODE == 1 && !skip_tile && blockIdx.x == 0 && g.gb_off >= 0) {  // bias gradient: the four k quarters of a row sit in adjacent lanes
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a = bsum[e];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        const int r = (tid + LOADERS * e) >> 2;
+        if ((tid & 3) == 0 && r < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r, a);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0 && !skip_tile) {  // ---------------------------------------------------- MMA issuer
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      for (int t = 0; t < n_stages; ++t) {
+        const int blk = t / BLK;
+        if (t % BLK == 0 && blk > 0) mbar_wait(blk_done, (uint32_t)(blk - 1) & 1u);  // the work accumulator has been drained
+        mbar_wait(full + t % LS, (uint32_t)(t / LS) & 1u);
+        tc_fence_after();
+        const uint32_t sr = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sl = smem_u32(lo + (size_t)(t % LS) * STAGE_BYTES);
+        const uint64_t da_hi = desc16(sr), db_hi = desc16(sr + A_BYTES), da_lo = desc16(sl), db_lo = desc16(sl + A_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < KS / 8; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * 16);  // two core matrices = 256 B
+          vmtc::mma_tf32(t_work, da_lo + adv, db_hi + adv, idesc, (t % BLK == 0 && ks == 0) ? 0u : 1u);
+          vmtc::mma_tf32(t_work, da_hi + adv, db_lo + adv, idesc, 1u);
+          vmtc::mma_tf32(t_work, da_hi + adv, db_hi + adv, idesc, 1u);
+        }
+        umma_commit(raw_empty + t % RS);
+        umma_commit(lo_empty + t % LS);
+        if (t % BLK == BLK - 1 || t == n_stages - 1) umma_commit(blk_full);
+      }
+    }
+  } else if (!skip_tile) {
+    // ------------------------------------------------------------------------ drain warps 9..12, then the epilogue
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      mbar_wait(blk_full, (uint32_t)blk & 1u);
+      tc_fence_after();
+      if (n_blocks > 1) {  // master (+)= work, round-to-nearest
+        for (int c0 = 0; c0 < n_tile; c0 += 32) {
+          uint32_t w[32], m[32];
+          tm_ld32(t_work + lane_addr + (uint32_t)c0, w);
+          if (blk > 0) tm_ld32(t_master + lane_addr + (uint32_t)c0, m);
+          tm_ld_wait();
+          if (blk > 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) + __uint_as_float(m[i]));
+          }
+          tm_st32(t_master + lane_addr + (uint32_t)c0, w);
+        }
+        tm_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(blk_done);
+    }
+    const uint32_t t_acc = (n_blocks > 1 ? t_master : t_work) + lane_addr;
+    tc_fence_after();
+    if (MODE == 0) {
+      const long long col = (long long)m0 + quarter * 32 + lane;  // this thread's sample
+      const int acc_row = g.pre_row >= 0 ? g.pre_row : g.out_row;
+      const int n_write = min(TN, g.n_out - n0);                   // padded outputs of this tile
+      vm::with_act(g.act, [&](auto tag) {
+        constexpr int ACT = decltype(tag)::value;
+        for (int c0 = 0; c0 < n_write; c0 += 32) {
+          uint32_t w[32];
+          if (n_stages > 0) { tm_ld32(t_acc + (uint32_t)c0, w); tm_ld_wait(); }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = n0 + c0 + i;
+            if (c0 + i < n_write) {
+              float x = (n_stages > 0 ? __uint_as_float(w[i]) : 0.0f) + (g.b_off >= 0 ? __ldg(g.par + g.b_off + j) : 0.0f);
+              if (g.accumulate) x += g.rows[(long long)(acc_row + j) * g.C + col];
+              if (g.pre_row >= 0) g.rows[(long long)(g.pre_row + j) * g.C + col] = x;
+              g.rows[(long long)(g.out_row + j) * g.C + col] = vm::act_fwd(ACT, x);
+            }
+          }
+        }
+      });
+    } else if (n_stages > 0) {
+      const int i = m0 + quarter * 32 + lane;  // TMEM lane = input feature
+      for (int c0 = 0; c0 < n_valid; c0 += 32) {
+        uint32_t w[32];
+        tm_ld32(t_acc + (uint32_t)c0, w);
+        tm_ld_wait();
+        if (i < g.n_in) {
+          float* dst = g.grad + g.w_off + (long long)i * g.ld + n0 + c0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (c0 + q < n_valid) atomicAdd(dst + q, __uint_as_float(w[q]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+}  // namespace vmg

@@ -22,6 +22,7 @@
 #include "vm_plan.h"
 #include "vm_tc.cuh"
 #include "vm_fused.cuh"
+#include "vm_gemm3.cuh"
 
 // ---- per-kernel timing (surj_profile_begin / surj_profile_end): every launch of the executor bracketed by events
 namespace prof {
@@ -479,7 +480,7 @@ Carve carve(const VmPlan* v, void* ws, int C, int prog) {
   k.scal_g = take(std::max(v->n_scalars, 1));
   k.loss = take(1);
   k.rows = take((size_t)v->n_rows * C);
-  static const bool pipe_mode = [] { const char* e = getenv("SURJ_B200_TC"); return !e || atoi(e) == 5; }();
+  static const bool pipe_mode = [] { const char* e = getenv("SURJ_B200_TC"); return !e || atoi(e) == 5 || atoi(e) == 6; }();
   const VmTcInfo& t = tc_info(v, prog);
   k.w_tiles = take(pipe_mode ? std::max<size_t>(t.w_floats, 1) : 1);
   k.a_tiles = take(pipe_mode ? std::max<size_t>((size_t)t.max_kpad * 2 * C, 1) : 1);
@@ -535,18 +536,22 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   const int C = chunk_cols(B, v->n_rows);
   Carve k = carve(v, ws, C, prog);
   static const int tc_mode = [] {
-    // 5 (default): TMA-fed pipelined tcgen05 LINEAR + tcgen05 LINEAR_DW; 1: register-staged tcgen05 for both;
+    // 6 (default): cp.async-fed, in-SM split 3xTF32 tcgen05 kernel for LINEAR and LINEAR_DW (vm_gemm3.cuh, no re-tiling pass);
+    // 5: TMA-fed pipelined tcgen05 LINEAR on re-tiled operands + register-staged tcgen05 LINEAR_DW; 1: register-staged tcgen05 for both;
     // 2 / 3: register-staged tcgen05 for LINEAR / LINEAR_DW only; 0: FP32 SIMT tiles only
     const char* e = getenv("SURJ_B200_TC");
-    return e ? atoi(e) : 5;
+    return e ? atoi(e) : 6;
   }();
-  const bool use_tc_lin = tc_mode == 1 || tc_mode == 2 || tc_mode == 5, use_tc_dw = tc_mode == 1 || tc_mode == 3 || tc_mode == 5;
+  const bool use_tc_lin = tc_mode == 1 || tc_mode == 2 || tc_mode == 5 || tc_mode == 6, use_tc_dw = tc_mode == 1 || tc_mode == 3 || tc_mode == 5;
+  const bool gemm3 = tc_mode == 6;
   static const bool use_tc = [] {
     const bool on = true;
     if (on) {
       cudaFuncSetAttribute(vmtc::vg_linear_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::PIPE_SMEM);
       cudaFuncSetAttribute(vmtc::vg_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::SMEM_BYTES);
       cudaFuncSetAttribute(vmtc::vg_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::SMEM_BYTES);
+      cudaFuncSetAttribute(vmg::vg_gemm3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
+      cudaFuncSetAttribute(vmg::vg_gemm3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
     }
     return on;
   }();
@@ -576,7 +581,13 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   // operands stream per 128x128 tile: 16 FLOP/B, profiles/r1_linear_pipe_ncu.md) but issues ~10x fewer instructions than
   // the register-staged kernel (SURJ_B200_TC=1), whose in-CTA split / staging is ALU-bound: measured at batch 262144,
   // train step cfg4 357 vs 413 ms, cfg5 349 vs 381 ms; log_prob 78 vs 100 and 73 vs 84 ms.
-  const bool pipe = use_tc && tc_mode == 5;
+  const bool pipe = use_tc && (tc_mode == 5 || tc_mode == 6);
+  // gradient phase of the backward program: everything after the base distribution's VJP.  Its products (training-mode
+  // recompute, input gradients, weight gradients) feed gradients only (bound 1e-4) and run on the 256-k-block kernel of
+  // vm_gemm3.cuh; products that feed log-probs (bound 1e-5) stay on the 16-k-block kernel (accumulator truncation bias).
+  size_t grad_from = ops.size();
+  for (size_t i = 0; i < ops.size(); ++i)
+    if (ops[i].code == vm::OP_BASE_BWD) { grad_from = i; break; }
   if (pipe) {
     std::map<long long, bool> done;
     for (size_t i = 0; i < ops.size(); ++i) {
@@ -655,7 +666,18 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
       }
       if (op.code == vm::OP_LINEAR) {
         const double fl = 2.0 * tci.nnz[pc] * (double)cols;
-        if (pipe && tci.w_off[pc] >= 0) {  // tcgen05 3xTF32, TMA-fed pipeline on pre-tiled operands
+        if (gemm3 && pc > grad_from && tc_linear_op(op)) {  // cp.async-fed 3xTF32 tcgen05 kernel straight from the rows and the staged weights
+          vmg::Args a{};
+          a.a_base = k.rows + (size_t)op.a[0] * C; a.a_pitch = C; a.a_rows = op.a[1];
+          a.b_base = k.par + op.a[10]; a.b_pitch = op.a[11]; a.b_rows = op.a[12];
+          a.K = op.a[1];
+          a.rows = k.rows; a.C = C; a.out_row = op.a[4]; a.pre_row = op.a[9]; a.n_out = op.a[5]; a.b_off = op.a[6]; a.act = op.a[7];
+          a.accumulate = op.a[8]; a.par = k.par;
+          a.kr = tci.kr[pc];
+          dim3 grid(cols / vmg::TM, (op.a[5] + vmg::TN - 1) / vmg::TN);
+          prof::Scope ps(st, prof::LINEAR_TC, fl);
+          vmg::vg_gemm3<0><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a);
+        } else if (pipe && tci.w_off[pc] >= 0) {  // tcgen05 3xTF32, TMA-fed pipeline on pre-tiled operands
           const int nkb = (op.a[1] + vmtc::PBK - 1) / vmtc::PBK;
           { prof::Scope ps(st, prof::TILE, 0.0);
           vmtc::vg_tile<true><<<dim3(cols / vmtc::TM, (op.a[1] + 31) / 32), 256, 0, st>>>(k.rows + (size_t)op.a[0] * C, (size_t)C,
@@ -677,7 +699,27 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
       } else if (op.code == vm::OP_LINEAR_DW) {
         const int NA = op.a[1] + (op.a[6] >= 0 ? 1 : 0), NG = op.a[3];
         const double fl = 2.0 * tci.nnz[pc] * (double)cols;
-        if (use_tc && use_tc_dw && NA >= 32 && NG >= 32) {
+        if (gemm3 && NA >= 32 && NG >= 32) {
+          vmg::Args a{};
+          a.a_base = k.rows + (size_t)op.a[0] * C; a.a_pitch = C; a.a_rows = op.a[1];
+          a.b_base = k.rows + (size_t)op.a[2] * C; a.b_pitch = C; a.b_rows = NG;
+          a.K = cols;
+          a.grad = k.grad; a.w_off = op.a[4]; a.ld = op.a[5]; a.gb_off = op.a[6]; a.n_in = op.a[1];
+          a.skip = tci.dw_skip[pc]; a.n_j128 = (NG + 127) / 128;
+          // sample slabs: the grid that wastes the least of its last wave (1 CTA per SM), slabs of >= 2048 samples
+          const int ti = (op.a[1] + vmg::TM - 1) / vmg::TM, tj = (NG + vmg::TN - 1) / vmg::TN, tiles = ti * tj;
+          int best_slabs = 1;
+          double best_util = 0.0;
+          for (int w = 1; w <= 8; ++w) {
+            const int slabs = std::min(std::max(1, v->n_sm * w / tiles), std::max(1, cols / 2048));
+            const double util = (double)tiles * slabs / ((double)v->n_sm * ((tiles * slabs + v->n_sm - 1) / v->n_sm));
+            if (util > best_util + 0.02) { best_util = util; best_slabs = slabs; }
+          }
+          a.k_slab = ((cols + best_slabs - 1) / best_slabs + 255) / 256 * 256;
+          dim3 grid(ti, tj, (cols + a.k_slab - 1) / a.k_slab);
+          prof::Scope ps(st, prof::DW_TC, fl);
+          vmg::vg_gemm3<1><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a);
+        } else if (use_tc && use_tc_dw && NA >= 32 && NG >= 32) {
           // sample slabs sized so the grid fills the machine about twice (2 CTAs per SM x 148 SMs x 2)
           // (the bias gradient comes out of staging the g operand, so the tile rows cover the n_in real inputs only)
           const int ti = (op.a[1] + vmtc::TM - 1) / vmtc::TM;
