@@ -508,31 +508,45 @@ def measure(ctx, cfg_name, batch, steps, warmup, pool=0, no_graph=False, e2e=Tru
     with torch.cuda.stream(ctx.stream):
       kinds = profile_kinds(lambda: w.step(0), ctx.dev)
     total_ms = sum(v["ms"] for v in kinds.values())
+    # tensor-pipe peak per kernel kind: FP32-grade products are THREE tensor-core MMAs, so peak = dense rate / 3.
+    #   kind::tf32 kernels (3xTF32: vm_gemm3.cuh, vm_tc.cuh)       dense TF32 tcgen05.mma rate measured in this run
+    #   kind::f16 kernel (fp16x3: vm_fused.cuh)                    MEASURED_PEAKS.json dense bf16/fp16 rate (sustained: the
+    #                                                              kernel runs inside a long step), else the fallback
+    f16_dense = float(peaks["file"].get("bf16_tflops_sustained", peaks["file"].get("bf16_tflops", 1670.0)))
+    f16_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks["file"] else "fallback 1670 (B200_PROFILING.md)"
     tensor_peak = peaks["tf32"] / 3.0
+
+    def peak_of(kind):
+      return (f16_dense / 3.0, f"{f16_src} ({f16_dense:.0f} TFLOP/s, kind::f16) / 3") if kind.startswith("fused_") else \
+             (tensor_peak, f"dense TF32 tcgen05.mma rate measured in this run (surj_bench_tf32_peak: {peaks['tf32']:.0f} TFLOP/s) / 3")
+
     top = max(kinds, key=lambda k: kinds[k]["ms"]) if kinds else None
     for k, v in kinds.items():
       v["share"] = v["ms"] / total_ms if total_ms > 0 else 0.0
       v["needed_tflops"] = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 and v["flops"] > 0 else None
+      if v["needed_tflops"] is not None and "tcgen05" in k:
+        v["peak_tflops"] = peak_of(k)[0]
+        v["frac"] = v["needed_tflops"] / v["peak_tflops"]
     if top is not None:
       t = kinds[top]
+      pk, pk_src = peak_of(top)
       per_launch_flops = t["flops"] / max(t["launches"], 1)
       per_launch_ms = t["ms"] / max(t["launches"], 1)
       ach = (t["flops"] / (t["ms"] * 1e-3) / 1e12) if t["flops"] > 0 else 0.0
       traffic = None
       try:
         tj = json.load(open(os.path.join(ROOT, "profiles", f"r2_{cfg_name}_top_traffic.json")))
-        traffic = tj.get("dram_bytes_per_launch")
+        traffic = tj.get(top, {}).get("dram_bytes_per_launch")
       except Exception:  # noqa: BLE001
         pass
       out["roofline"] = {
         "kernel": f"{top} (per-op executor; {t['launches']} launches, {100 * t['share']:.1f} % of the train step)",
-        "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak if tensor_peak else None,
-        "peak_source": (f"dense TF32 tcgen05.mma rate measured in this run (surj_bench_tf32_peak: {peaks['tf32']:.0f} TFLOP/s) / 3 -- "
-                        "FP32-grade products are 3 tensor-core MMAs; numerator = NEEDED FLOPs (structural zeros excluded)"),
+        "bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk if pk else None,
+        "peak_source": pk_src + " -- FP32-grade products are 3 tensor-core MMAs; numerator = NEEDED FLOPs (structural zeros excluded)",
         "flops_per_launch": per_launch_flops, "us_per_launch": 1e3 * per_launch_ms, "traffic": traffic,
         "whole_step": {"achieved": step_flops / (out["ms_per_step"] * 1e-3) / 1e12, "peak": tensor_peak,
                        "frac": step_flops / (out["ms_per_step"] * 1e-3) / 1e12 / tensor_peak if tensor_peak else None,
-                       "flops": step_flops},
+                       "flops": step_flops, "peak_note": "TF32 / 3 for the whole step (most of its products are 3xTF32)"},
         "kernels": kinds,
       }
   _dbg(f"{cfg_name}: roofline done")

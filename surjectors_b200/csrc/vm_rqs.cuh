@@ -156,6 +156,7 @@ struct RqsGrad {
 VM_DEV void rqs_bwd_core(const RqsBin& b, int K, float lo, float hi, float v, bool forward, float g_out, float g_ld, RqsGrad& G) {
   float g_v, gx0 = 0.0f, gx1 = 0.0f, gy0 = 0.0f, gy1 = 0.0f, gd0 = 0.0f, gd1 = 0.0f;
   G.ks = -1;
+  G.g_tail = G.Aw = G.Bw = G.dotw = G.Ah = G.Bh = G.doth = G.g_u0 = G.g_u1 = 0.0f;  // (a tail leaves the in-range coefficients unused: defined, so that a caller may multiply them by zero)
   if (b.bin < 0 || b.bin >= K) {
     const float e = b.bin < 0 ? lo : hi;
     float gd;
