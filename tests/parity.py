@@ -184,15 +184,18 @@ def _check_config(name, batch, device, check_grad, seed, w_std, b_val=None, y_ov
     loss, grads = value_and_grad(loss_fn)(params)
     oloss, ograds, _ = oad.value_and_grad(om, oparams, **ob)
     le = abs(float(loss) - float(oloss)) / max(1.0, abs(float(oloss)))
-    assert le <= 1e-5, f"{name}: loss relative error {le:.3e}"
     ge = grad_errors(grads, ograds)
     gtol = {n: GRAD_RTOL for n in ge}
+    ltol = 1e-5
     if fp32_slack:
       om32, p32, b32 = _oracle32(name, oparams, ob, scale)
-      _, g32, _ = oad.value_and_grad(om32, p32, **b32)
+      l32, g32, _ = oad.value_and_grad(om32, p32, **b32)
+      ltol = max(ltol, 2.0 * abs(float(l32) - float(oloss)) / max(1.0, abs(float(oloss))))
+      out["loss_fp32_oracle_err"] = abs(float(l32) - float(oloss)) / max(1.0, abs(float(oloss)))
       ge32 = grad_errors(g32, ograds)
       gtol = {n: max(GRAD_RTOL, 2.0 * max(ge32.values())) for n in ge}
       out["grad_fp32_oracle_err"] = max(ge32.values())
+    assert le <= ltol, f"{name}: loss relative error {le:.3e} (bound {ltol:.3e})"
     worst = max(ge, key=lambda n: ge[n] / gtol[n])
     assert ge[worst] <= gtol[worst], f"{name}: gradient error {ge[worst]:.3e} at {worst} (bound {gtol[worst]:.3e})"
     out["grad_err"] = ge[worst]
