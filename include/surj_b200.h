@@ -219,6 +219,12 @@ int surj_train_step_dp(const SurjPlan* plan, SurjDp* dp, SurjStream stream, cons
 int64_t surj_made_masks(int32_t n_params, int32_t input_size, const int32_t* hidden, int32_t n_hidden, uint8_t* out);
 /* Permutation inverse index exactly as permutation.py:31-36 computes it (int32). */
 int surj_permutation_inverse(const int32_t* permutation, int32_t n, int32_t* inverse_out);
+/* as_batch_iterator's batch selection (surjectors/util.py:88-95, lax.index_take on axis 0) on the device:
+ * dst[r][:] = src[idx[first + r]][:] for r < n_take; src is [n_rows, width] float32, idx int32 (all device pointers).
+ * Bit-exact copy, enqueue-only.  An index outside [0, n_rows) writes a zero row and sets *err_flag (device int32, may be
+ * NULL) to 1 instead of reading out of bounds. */
+int surj_index_take(SurjStream stream, const float* src, int64_t n_rows, int32_t width, const int32_t* idx, int64_t first,
+                    int64_t n_take, float* dst, int32_t* err_flag);
 
 /* --- measurement helper (bench.py): a register-only FFMA loop, 16 independent chains per thread,
  * launched over every SM; *flops_out = floating-point operations one launch executes.  Gives the

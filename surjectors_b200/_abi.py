@@ -119,6 +119,7 @@ _SIGNATURES = {
                                    C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
   "surj_made_masks": (C.c_int64, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8)]),
   "surj_permutation_inverse": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+  "surj_index_take": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
   "surj_bench_fp32_peak": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]),
   "surj_bench_tf32_peak": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]),
   "surj_profile_begin": (C.c_int, []),

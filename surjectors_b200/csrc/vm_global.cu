@@ -666,7 +666,9 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
       }
       if (op.code == vm::OP_LINEAR) {
         const double fl = 2.0 * tci.nnz[pc] * (double)cols;
-        if (gemm3 && pc > grad_from && tc_linear_op(op)) {  // cp.async-fed 3xTF32 tcgen05 kernel straight from the rows and the staged weights
+        // (long contractions only -- the input gradient through a spline layer's 1544 .. 6176 thetas; on K <= 512 its
+        // one-tile-per-CTA set-up costs more than it saves: cfg5's MADE layers measured 777 vs 520 ms per train step)
+        if (gemm3 && pc > grad_from && tc_linear_op(op) && op.a[1] >= 1024) {  // cp.async-fed 3xTF32 tcgen05 kernel straight from the rows and the staged weights
           vmg::Args a{};
           a.a_base = k.rows + (size_t)op.a[0] * C; a.a_pitch = C; a.a_rows = op.a[1];
           a.b_base = k.par + op.a[10]; a.b_pitch = op.a[11]; a.b_rows = op.a[12];
