@@ -37,18 +37,23 @@ using vmtc::tc_fence_after;
 using vmtc::tc_fence_before;
 using vmtc::umma_commit;
 
+// k per stage, ring depths: bytes in flight are what this kernel lives on.  Measured on the gradient-phase products of a
+// cfg4 train step (weight gradients / input gradients, ms): KS 16, RS 4, LS 3 (72 KB in flight): 209 / 202;
+// KS 32, RS 2, LS 2 (full cache lines per row piece, but 48 KB in flight): 316 / 258.
 constexpr int TM = 128, TN = 256, KS = 16;     // tile, k per stage
-constexpr int BLK = 16;                        // stages per accumulation block inside the tensor core (256 k)
-constexpr int RS = 4, LS = 3;                  // raw / lo ring depths
+constexpr int BLK = 256 / KS;                  // stages per accumulation block inside the tensor core (256 k)
+constexpr int RS = 6, LS = 2;                  // raw / lo ring depths
+constexpr int KQ = KS / 4;                     // 16-byte pieces per row and stage
 constexpr int A_BYTES = TM * KS * 4, B_BYTES = TN * KS * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int LOADERS = 256, THREADS = 416;
 constexpr size_t SMEM_BYTES = 1024 + (size_t)(RS + LS) * STAGE_BYTES + 256;
+static_assert(SMEM_BYTES <= 227 * 1024, "rings exceed the shared memory of an SM");
 
-__device__ __forceinline__ uint32_t soff(int r, int k) {  // byte offset of element (r, k) in a [rows x 16] K-major tile
-  return (uint32_t)((r >> 3) * 512 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
+__device__ __forceinline__ uint32_t soff(int r, int k) {  // byte offset of element (r, k) in a [rows x KS] K-major tile
+  return (uint32_t)((r >> 3) * (KQ * 128) + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
 }
-__device__ __forceinline__ uint64_t desc16(uint32_t saddr) {  // LBO 128 B, SBO 512 B (4 core matrices of 4 k per 8-row group)
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | (32ull << 32) | (1ull << 46);
+__device__ __forceinline__ uint64_t desc16(uint32_t saddr) {  // LBO 128 B, SBO = KQ core matrices of 4 k per 8-row group
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | ((uint64_t)(KQ * 8) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void cp16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -131,8 +136,8 @@ vg_gemm3(const __grid_constant__ Args g) {
         const int tl = 2 * (int)blockIdx.y + half;
         if (tl < 8 && half * 128 < n_valid && g.kr.hi[tl] > g.kr.lo[tl]) { l = min(l, (int)g.kr.lo[tl]); h = max(h, (int)g.kr.hi[tl]); }
       }
-      k_begin = h > 0 ? l * KS : 0;
-      k_end = h > 0 ? min(g.K, h * KS) : 0;
+      k_begin = h > 0 ? l * 16 : 0;  // (the ranges are in 16-k blocks: vm_global.cu tc_info)
+      k_end = h > 0 ? min(g.K, h * 16) : 0;
     }
   } else {
     m0 = blockIdx.x * TM;                                // first input feature of the tile
@@ -172,17 +177,22 @@ vg_gemm3(const __grid_constant__ Args g) {
     // A tile 128 x 16 floats = 512 pieces of 16 B (2 per thread); B tile 256 x 16 = 1024 pieces (4 per thread);
     // piece q -> row q / 4, k quarter q % 4 (K-major sources).  LINEAR's A is sample-major: element-wise 4-byte copies,
     // thread -> sample tid % 128, k quarters tid / 128 and tid / 128 + 2.
-    // (Measured alternative: two sets of four warps taking the stages in turn, each with two stage times for its
-    // landed -> split -> fence -> arrive -> refill chain, but only one stage in flight per set: 286 vs 209 ms for the
-    // weight-gradient products of a cfg4 train step -- bytes in flight matter more than the chain's latency.)
-    float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // DW: running sums of this thread's four g rows (bias gradient)
+    // (Measured alternatives, weight-gradient / input-gradient products of a cfg4 train step in ms against 203 / 197 for
+    // this version: two sets of four warps taking the stages in turn, one stage in flight per set: 286 / 230; lanes 0..3 /
+    // 4..7 of every group of eight owning even / odd stages so that a warp instruction covers whole 128-byte lines, two
+    // stages in flight per set: 348 / 208; 32-k stages with two raw slots: 316 / 258.  Every thread taking part in
+    // every stage, with as many stages in flight as shared memory holds, wins.)
+    constexpr int PA = TM * KQ / LOADERS, PB = TN * KQ / LOADERS;  // pieces per thread and stage (A: 2, B: 4)
+    float bsum[PB];  // DW: running sums of this thread's g rows (bias gradient)
+#pragma unroll
+    for (int e = 0; e < PB; ++e) bsum[e] = 0.0f;
     auto issue = [&](int t) {
       const int k0 = k_begin + t * KS;
       const uint32_t sa = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sb = sa + A_BYTES;
-      if (MODE == 0) {
+      if (MODE == 0) {  // sample-major source: a thread fills whole 16-byte pieces (sample tid % 128, k quarters tid / 128 + 2 e)
         const int s = tid & 127;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+        for (int e = 0; e < PA; ++e) {
           const int kq = (tid >> 7) + 2 * e;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -193,16 +203,16 @@ vg_gemm3(const __grid_constant__ Args g) {
         }
       } else {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int q = tid + LOADERS * e, r = q >> 2, kq = q & 3;
+        for (int e = 0; e < PA; ++e) {
+          const int q = tid + LOADERS * e, r = q / KQ, kq = q % KQ;
           const int kk = k0 + 4 * kq;
           const int nb = (r < m_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
           cp16(sa + soff(r, 4 * kq), g.a_base + (long long)(nb ? m0 + r : 0) * g.a_pitch + (nb ? kk : 0), nb);
         }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int q = tid + LOADERS * e, r = q >> 2, kq = q & 3;
+      for (int e = 0; e < PB; ++e) {
+        const int q = tid + LOADERS * e, r = q / KQ, kq = q % KQ;
         const int kk = k0 + 4 * kq;
         const int nb = (r < n_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
         if (r < n_tile) cp16(sb + soff(r, 4 * kq), g.b_base + (long long)(nb ? n0 + r : 0) * g.b_pitch + (nb ? kk : 0), nb);
@@ -223,18 +233,18 @@ vg_gemm3(const __grid_constant__ Args g) {
       };
       if (MODE == 0) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) one(soff(tid & 127, 4 * ((tid >> 7) + 2 * e)), nullptr);
+        for (int e = 0; e < PA; ++e) one(soff(tid & 127, 4 * ((tid >> 7) + 2 * e)), nullptr);
       } else {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+        for (int e = 0; e < PA; ++e) {
           const int q = tid + LOADERS * e;
-          one(soff(q >> 2, 4 * (q & 3)), nullptr);
+          one(soff(q / KQ, 4 * (q % KQ)), nullptr);
         }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int q = tid + LOADERS * e, r = q >> 2;
-        if (r < n_tile) one(A_BYTES + soff(r, 4 * (q & 3)), MODE == 1 ? &bsum[e] : nullptr);
+      for (int e = 0; e < PB; ++e) {
+        const int q = tid + LOADERS * e, r = q / KQ;
+        if (r < n_tile) one(A_BYTES + soff(r, 4 * (q % KQ)), MODE == 1 ? &bsum[e] : nullptr);
       }
     };
     if (!skip_tile) {
@@ -268,14 +278,14 @@ vg_gemm3(const __grid_constant__ Args g) {
         if (lane == 0) atomicAdd(g.grad + g.gb_off + n0 + j, a);
       }
     }
-    if (MODE == 1 && !skip_tile && blockIdx.x == 0 && g.gb_off >= 0) {  // bias gradient: the four k quarters of a row sit in adjacent lanes
+    if (MODE == 1 && !skip_tile && blockIdx.x == 0 && g.gb_off >= 0) {  // bias gradient: the KQ pieces of a row sit in adjacent lanes
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < PB; ++e) {
         float a = bsum[e];
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        const int r = (tid + LOADERS * e) >> 2;
-        if ((tid & 3) == 0 && r < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r, a);
+#pragma unroll
+        for (int o = 1; o < KQ; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        const int r = (tid + LOADERS * e) / KQ;
+        if ((tid % KQ) == 0 && r < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r, a);
       }
     }
   } else if (warp == 8) {
