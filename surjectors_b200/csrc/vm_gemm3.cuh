@@ -89,6 +89,15 @@ __device__ __forceinline__ void tm_st32(uint32_t taddr, const uint32_t (&r)[32])
 __device__ __forceinline__ void tm_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tm_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// piece q of a K-major [rows x 16] tile -> (row, k quarter) such that EIGHT CONSECUTIVE LANES hold the same k quarter of
+// eight consecutive rows: their 16-byte shared-memory accesses are 128 contiguous bytes (one conflict-free wavefront).
+// (row = q / 4, quarter = q % 4 -- contiguous along k -- puts four lanes on the same banks: every LDGSTS / LDS / STS of
+// the loaders took four times its wavefronts and the MMA issuer waited for the loaders 62 % of its time.)
+__device__ __forceinline__ void piece_of(int q, int& r, int& kq) {
+  r = (q & 7) | ((q >> 5) << 3);
+  kq = (q >> 3) & 3;
+}
+
 struct Args {
   // operands
   const float* a_base; long long a_pitch; int a_rows;  // LINEAR: in rows [k][sample] (+ sample offset), a_rows = K;  DW: in rows [i][sample], a_rows = valid i
@@ -104,6 +113,8 @@ struct Args {
   VmKRange kr;                                         // LINEAR: k-stage range per 128-output tile (structural zeros), by value
   unsigned long long skip;                             // DW: all-zero 128 x 128 tiles (bit i_tile * n_j128 + j128_tile)
   int n_j128;
+  long long* dbg;                                      // SURJ_B200_FUSED_DBG=1: CTA (0,0,0)'s MMA issuer adds [10] cycles waiting for a split stage,
+                                                       // [11] for the drain of a block, [12] its total cycles
 };
 
 // MODE 0: LINEAR, grid (sample tiles, ceil(n_out / 256)).   MODE 1: LINEAR_DW, grid (ceil(n_in / 128), ceil(n_out / 256), slabs).
@@ -189,22 +200,19 @@ vg_gemm3(const __grid_constant__ Args g) {
     auto issue = [&](int t) {
       const int k0 = k_begin + t * KS;
       const uint32_t sa = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sb = sa + A_BYTES;
-      if (MODE == 0) {  // sample-major source: a thread fills whole 16-byte pieces (sample tid % 128, k quarters tid / 128 + 2 e)
-        const int s = tid & 127;
+      if (MODE == 0) {  // sample-major source, element-wise copies: a warp instruction moves 8 samples x the 4 k of one quarter
+                        // (32 distinct banks; 4 sectors of 32 B in memory); warp w, step e -> sample group (8 w + e) / 4, quarter (8 w + e) % 4
 #pragma unroll
-        for (int e = 0; e < PA; ++e) {
-          const int kq = (tid >> 7) + 2 * e;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int k = 4 * kq + i;
-            const bool ok = k0 + k < k_end;
-            cp4(sa + soff(s, k), g.a_base + (long long)(ok ? k0 + k : 0) * g.a_pitch + m0 + s, ok ? 4 : 0);
-          }
+        for (int e = 0; e < 8; ++e) {
+          const int c = 8 * warp + e, smp = ((c >> 2) << 3) | (lane & 7), k = 4 * (c & 3) + (lane >> 3);
+          const bool ok = k0 + k < k_end;
+          cp4(sa + soff(smp, k), g.a_base + (long long)(ok ? k0 + k : 0) * g.a_pitch + m0 + smp, ok ? 4 : 0);
         }
       } else {
 #pragma unroll
         for (int e = 0; e < PA; ++e) {
-          const int q = tid + LOADERS * e, r = q / KQ, kq = q % KQ;
+          int r, kq;
+          piece_of(tid + LOADERS * e, r, kq);
           const int kk = k0 + 4 * kq;
           const int nb = (r < m_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
           cp16(sa + soff(r, 4 * kq), g.a_base + (long long)(nb ? m0 + r : 0) * g.a_pitch + (nb ? kk : 0), nb);
@@ -212,7 +220,8 @@ vg_gemm3(const __grid_constant__ Args g) {
       }
 #pragma unroll
       for (int e = 0; e < PB; ++e) {
-        const int q = tid + LOADERS * e, r = q / KQ, kq = q % KQ;
+        int r, kq;
+        piece_of(tid + LOADERS * e, r, kq);
         const int kk = k0 + 4 * kq;
         const int nb = (r < n_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
         if (r < n_tile) cp16(sb + soff(r, 4 * kq), g.b_base + (long long)(nb ? n0 + r : 0) * g.b_pitch + (nb ? kk : 0), nb);
@@ -231,20 +240,26 @@ vg_gemm3(const __grid_constant__ Args g) {
         *reinterpret_cast<float4*>(sl + off) = l;
         if (sum != nullptr) *sum += (x.x + x.y) + (x.z + x.w);
       };
-      if (MODE == 0) {
+      if (MODE == 0) {  // the warp splits the 64 pieces it copied (the 4 k of a piece came from 4 lanes: warp-level sync first)
+        __syncwarp();
 #pragma unroll
-        for (int e = 0; e < PA; ++e) one(soff(tid & 127, 4 * ((tid >> 7) + 2 * e)), nullptr);
+        for (int j = 0; j < 2; ++j) {
+          const int pi = lane + 32 * j, c = 8 * warp + (pi >> 3);
+          one(soff(((c >> 2) << 3) | (pi & 7), 4 * (c & 3)), nullptr);
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < PA; ++e) {
-          const int q = tid + LOADERS * e;
-          one(soff(q / KQ, 4 * (q % KQ)), nullptr);
+          int r, kq;
+          piece_of(tid + LOADERS * e, r, kq);
+          one(soff(r, 4 * kq), nullptr);
         }
       }
 #pragma unroll
       for (int e = 0; e < PB; ++e) {
-        const int q = tid + LOADERS * e, r = q / KQ;
-        if (r < n_tile) one(A_BYTES + soff(r, 4 * (q % KQ)), MODE == 1 ? &bsum[e] : nullptr);
+        int r, kq;
+        piece_of(tid + LOADERS * e, r, kq);
+        if (r < n_tile) one(A_BYTES + soff(r, 4 * kq), MODE == 1 ? &bsum[e] : nullptr);
       }
     };
     if (!skip_tile) {
@@ -278,23 +293,30 @@ vg_gemm3(const __grid_constant__ Args g) {
         if (lane == 0) atomicAdd(g.grad + g.gb_off + n0 + j, a);
       }
     }
-    if (MODE == 1 && !skip_tile && blockIdx.x == 0 && g.gb_off >= 0) {  // bias gradient: the KQ pieces of a row sit in adjacent lanes
+    if (MODE == 1 && !skip_tile && blockIdx.x == 0 && g.gb_off >= 0) {  // bias gradient: a row's four k quarters sit in lanes l, l + 8, l + 16, l + 24
 #pragma unroll
       for (int e = 0; e < PB; ++e) {
         float a = bsum[e];
-#pragma unroll
-        for (int o = 1; o < KQ; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        const int r = (tid + LOADERS * e) / KQ;
-        if ((tid % KQ) == 0 && r < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r, a);
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 16);
+        int r, kq;
+        piece_of(tid + LOADERS * e, r, kq);
+        if (kq == 0 && r < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r, a);
       }
     }
   } else if (warp == 8) {
     if (lane == 0 && !skip_tile) {  // ---------------------------------------------------- MMA issuer
+      const bool rec = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long w_full = 0, w_blk = 0;
+      const long long t_start = rec ? clock64() : 0;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       for (int t = 0; t < n_stages; ++t) {
         const int blk = t / BLK;
+        long long c0 = rec ? clock64() : 0;
         if (t % BLK == 0 && blk > 0) mbar_wait(blk_done, (uint32_t)(blk - 1) & 1u);  // the work accumulator has been drained
+        long long c1 = rec ? clock64() : 0;
         mbar_wait(full + t % LS, (uint32_t)(t / LS) & 1u);
+        if (rec) { w_blk += c1 - c0; w_full += clock64() - c1; }
         tc_fence_after();
         const uint32_t sr = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sl = smem_u32(lo + (size_t)(t % LS) * STAGE_BYTES);
         const uint64_t da_hi = desc16(sr), db_hi = desc16(sr + A_BYTES), da_lo = desc16(sl), db_lo = desc16(sl + A_BYTES);
@@ -308,6 +330,12 @@ vg_gemm3(const __grid_constant__ Args g) {
         umma_commit(raw_empty + t % RS);
         umma_commit(lo_empty + t % LS);
         if (t % BLK == BLK - 1 || t == n_stages - 1) umma_commit(blk_full);
+      }
+      if (rec) {
+        atomicAdd((unsigned long long*)g.dbg + 10, (unsigned long long)w_full);
+        atomicAdd((unsigned long long*)g.dbg + 11, (unsigned long long)w_blk);
+        atomicAdd((unsigned long long*)g.dbg + 12, (unsigned long long)(clock64() - t_start));
+        atomicAdd((unsigned long long*)g.dbg + 13, (unsigned long long)n_stages);
       }
     }
   } else if (!skip_tile) {

@@ -72,6 +72,7 @@ extern "C" int64_t surj_profile_end(char* out, int64_t out_bytes) {
     cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[fused dbg, CTA 0, cycles] producer waits free slot %lld | MMA waits weights %lld, accumulator %lld, operand %lld | "
             "epilogue warp 2: waits accumulator %lld, hidden phases %lld, bias staging %lld, input load %lld, spline %lld | CTA total %lld\n", h[0], h[1], h[2], h[3], h[4], h[6], h[7], h[9], h[8], h[5]);
+    fprintf(stderr, "[gemm3 dbg, CTA 0 MMA issuer, cycles] waits split stage %lld, waits block drain %lld, total %lld, stages %lld\n", h[10], h[11], h[12], h[13]);
   }
   double ms[prof::N_KINDS] = {0}, fl[prof::N_KINDS] = {0};
   long long n[prof::N_KINDS] = {0};
@@ -676,6 +677,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           a.rows = k.rows; a.C = C; a.out_row = op.a[4]; a.pre_row = op.a[9]; a.n_out = op.a[5]; a.b_off = op.a[6]; a.act = op.a[7];
           a.accumulate = op.a[8]; a.par = k.par;
           a.kr = tci.kr[pc];
+          a.dbg = fused_dbg_buffer();
           dim3 grid(cols / vmg::TM, (op.a[5] + vmg::TN - 1) / vmg::TN);
           prof::Scope ps(st, prof::LINEAR_TC, fl);
           vmg::vg_gemm3<0><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a);
@@ -708,6 +710,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           a.K = cols;
           a.grad = k.grad; a.w_off = op.a[4]; a.ld = op.a[5]; a.gb_off = op.a[6]; a.n_in = op.a[1];
           a.skip = tci.dw_skip[pc]; a.n_j128 = (NG + 127) / 128;
+          a.dbg = fused_dbg_buffer();
           // sample slabs: the grid that wastes the least of its last wave (1 CTA per SM), slabs of >= 2048 samples
           const int ti = (op.a[1] + vmg::TM - 1) / vmg::TM, tj = (NG + vmg::TN - 1) / vmg::TN, tiles = ti * tj;
           int best_slabs = 1;
