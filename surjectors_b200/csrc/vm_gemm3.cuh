@@ -126,7 +126,7 @@ vg_gemm3(const __grid_constant__ Args g) {
   unsigned char* raw = base;                                  // [RS][A | B]
   unsigned char* lo = base + (size_t)RS * STAGE_BYTES;        // [LS][A | B]
   uint64_t* bars = (uint64_t*)(lo + (size_t)LS * STAGE_BYTES);
-  uint64_t* full = bars;             // [LS]  256 arrivals: stage split and visible
+  uint64_t* full = bars;             // [LS]  128 arrivals (the warp set that owns the stage): split and visible
   uint64_t* lo_empty = full + LS;    // [LS]  MMA commit
   uint64_t* raw_empty = lo_empty + LS;  // [RS] MMA commit
   uint64_t* blk_full = raw_empty + RS;  // [1]  MMA commit: a block's accumulator is complete
@@ -166,7 +166,7 @@ vg_gemm3(const __grid_constant__ Args g) {
   }
 
   if (tid == 0) {
-    for (int s = 0; s < LS; ++s) { mbar_init(full + s, LOADERS); mbar_init(lo_empty + s, 1); }
+    for (int s = 0; s < LS; ++s) { mbar_init(full + s, LOADERS / 2); mbar_init(lo_empty + s, 1); }
     for (int s = 0; s < RS; ++s) mbar_init(raw_empty + s, 1);
     mbar_init(blk_full, 1);
     mbar_init(blk_done, 4);
@@ -193,7 +193,11 @@ vg_gemm3(const __grid_constant__ Args g) {
     // 4..7 of every group of eight owning even / odd stages so that a warp instruction covers whole 128-byte lines, two
     // stages in flight per set: 348 / 208; 32-k stages with two raw slots: 316 / 258.  Every thread taking part in
     // every stage, with as many stages in flight as shared memory holds, wins.)
-    constexpr int PA = TM * KQ / LOADERS, PB = TN * KQ / LOADERS;  // pieces per thread and stage (A: 2, B: 4)
+    // Two sets of four warps take the stages in turn (set = warp / 4 owns stages set, set + 2, ...): the per-stage chain
+    // landed -> split -> proxy fence -> arrive -> refill is latency, not throughput, so two sets halve its cost per stage.
+    // Each set keeps two stages in flight behind the one it is splitting (three of the six raw slots).
+    const int set = warp >> 2, ts = tid & 127, wq = warp & 3;
+    constexpr int PA = TM * KQ / (LOADERS / 2), PB = TN * KQ / (LOADERS / 2);  // pieces per thread and owned stage (A: 4, B: 8)
     float bsum[PB];  // DW: running sums of this thread's g rows (bias gradient)
 #pragma unroll
     for (int e = 0; e < PB; ++e) bsum[e] = 0.0f;
@@ -201,10 +205,10 @@ vg_gemm3(const __grid_constant__ Args g) {
       const int k0 = k_begin + t * KS;
       const uint32_t sa = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sb = sa + A_BYTES;
       if (MODE == 0) {  // sample-major source, element-wise copies: a warp instruction moves 8 samples x the 4 k of one quarter
-                        // (32 distinct banks; 4 sectors of 32 B in memory); warp w, step e -> sample group (8 w + e) / 4, quarter (8 w + e) % 4
+                        // (32 distinct banks; 4 sectors of 32 B in memory); warp w of the set, step e -> sample group (16 w + e) / 4, quarter (16 w + e) % 4
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = 8 * warp + e, smp = ((c >> 2) << 3) | (lane & 7), k = 4 * (c & 3) + (lane >> 3);
+        for (int e = 0; e < 16; ++e) {
+          const int c = 16 * wq + e, smp = ((c >> 2) << 3) | (lane & 7), k = 4 * (c & 3) + (lane >> 3);
           const bool ok = k0 + k < k_end;
           cp4(sa + soff(smp, k), g.a_base + (long long)(ok ? k0 + k : 0) * g.a_pitch + m0 + smp, ok ? 4 : 0);
         }
@@ -212,7 +216,7 @@ vg_gemm3(const __grid_constant__ Args g) {
 #pragma unroll
         for (int e = 0; e < PA; ++e) {
           int r, kq;
-          piece_of(tid + LOADERS * e, r, kq);
+          piece_of(ts + 128 * e, r, kq);
           const int kk = k0 + 4 * kq;
           const int nb = (r < m_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
           cp16(sa + soff(r, 4 * kq), g.a_base + (long long)(nb ? m0 + r : 0) * g.a_pitch + (nb ? kk : 0), nb);
@@ -221,7 +225,7 @@ vg_gemm3(const __grid_constant__ Args g) {
 #pragma unroll
       for (int e = 0; e < PB; ++e) {
         int r, kq;
-        piece_of(tid + LOADERS * e, r, kq);
+        piece_of(ts + 128 * e, r, kq);
         const int kk = k0 + 4 * kq;
         const int nb = (r < n_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
         if (r < n_tile) cp16(sb + soff(r, 4 * kq), g.b_base + (long long)(nb ? n0 + r : 0) * g.b_pitch + (nb ? kk : 0), nb);
@@ -240,42 +244,42 @@ vg_gemm3(const __grid_constant__ Args g) {
         *reinterpret_cast<float4*>(sl + off) = l;
         if (sum != nullptr) *sum += (x.x + x.y) + (x.z + x.w);
       };
-      if (MODE == 0) {  // the warp splits the 64 pieces it copied (the 4 k of a piece came from 4 lanes: warp-level sync first)
+      if (MODE == 0) {  // the warp splits the 128 pieces it copied (the 4 k of a piece came from 4 lanes: warp-level sync first)
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int pi = lane + 32 * j, c = 8 * warp + (pi >> 3);
+        for (int j = 0; j < 4; ++j) {
+          const int pi = lane + 32 * j, c = 16 * wq + (pi >> 3);
           one(soff(((c >> 2) << 3) | (pi & 7), 4 * (c & 3)), nullptr);
         }
       } else {
 #pragma unroll
         for (int e = 0; e < PA; ++e) {
           int r, kq;
-          piece_of(tid + LOADERS * e, r, kq);
+          piece_of(ts + 128 * e, r, kq);
           one(soff(r, 4 * kq), nullptr);
         }
       }
 #pragma unroll
       for (int e = 0; e < PB; ++e) {
         int r, kq;
-        piece_of(tid + LOADERS * e, r, kq);
+        piece_of(ts + 128 * e, r, kq);
         if (r < n_tile) one(A_BYTES + soff(r, 4 * kq), MODE == 1 ? &bsum[e] : nullptr);
       }
     };
     if (!skip_tile) {
-      // RS - 1 stages in flight.  The refill of a slot is issued at the END of an iteration (it waits for the MMAs of the
-      // previous stage, which have had a whole split to finish), so splitting stage t + 1 overlaps the MMAs of stage t.
-      for (int t = 0; t < RS - 1; ++t) {
+      // per set: the stage being split plus two in flight; the refill of a slot is issued at the END of an iteration (it
+      // waits for the MMAs of this set's previous stage, which have had two stage times to finish)
+      for (int t = set; t < set + 4; t += 2) {
         if (t < n_stages) issue(t);
         cp_commit();
       }
-      for (int t = 0; t < n_stages; ++t) {
-        cp_wait<RS - 2>();                                   // this thread's pieces of stage t have landed
+      for (int t = set; t < n_stages; t += 2) {
+        cp_wait<1>();                                        // this thread's pieces of stage t have landed
         if (t >= LS) mbar_wait(lo_empty + t % LS, (uint32_t)(t / LS - 1) & 1u);
         split(t);
         fence_async_smem();
         mbar_arrive(full + t % LS);
-        const int tn = t + RS - 1;                           // refill the slot stage t - 1 used
+        const int tn = t + 4;                                // into the slot this set's stage t - 2 used
         if (tn < n_stages) {
           if (tn >= RS) mbar_wait(raw_empty + tn % RS, (uint32_t)(tn / RS - 1) & 1u);
           issue(tn);
@@ -300,7 +304,7 @@ vg_gemm3(const __grid_constant__ Args g) {
         a += __shfl_xor_sync(0xffffffffu, a, 8);
         a += __shfl_xor_sync(0xffffffffu, a, 16);
         int r, kq;
-        piece_of(tid + LOADERS * e, r, kq);
+        piece_of(ts + 128 * e, r, kq);
         if (kq == 0 && r < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r, a);
       }
     }
