@@ -244,7 +244,7 @@ int surj_profile_begin(void);
 int64_t surj_profile_end(char* out, int64_t out_bytes);
 
 /* --- tuning / test knob of the per-op executor: the number of samples whose rows are resident in the workspace at a
- * time (rounded up to 128; default 131072, SURJ_B200_CHUNK at load time; 0 restores the default).  Returns the
+ * time (rounded up to 128; default 262144, SURJ_B200_CHUNK at load time; 0 restores the default).  Returns the
  * previous value.  Changes surj_plan_workspace_bytes: query it again after setting. */
 int64_t surj_set_chunk_samples(int64_t samples);
 /* the fused conditioner + spline kernel of the per-op executor on (1, default; SURJ_B200_FUSION at load time) / off (0:

@@ -126,7 +126,7 @@ vg_gemm3(const __grid_constant__ Args g) {
   unsigned char* raw = base;                                  // [RS][A | B]
   unsigned char* lo = base + (size_t)RS * STAGE_BYTES;        // [LS][A | B]
   uint64_t* bars = (uint64_t*)(lo + (size_t)LS * STAGE_BYTES);
-  uint64_t* full = bars;             // [LS]  128 arrivals (the warp set that owns the stage): split and visible
+  uint64_t* full = bars;             // [LS]  4 arrivals (the warps of the set that owns the stage): split and visible
   uint64_t* lo_empty = full + LS;    // [LS]  MMA commit
   uint64_t* raw_empty = lo_empty + LS;  // [RS] MMA commit
   uint64_t* blk_full = raw_empty + RS;  // [1]  MMA commit: a block's accumulator is complete
@@ -166,7 +166,7 @@ vg_gemm3(const __grid_constant__ Args g) {
   }
 
   if (tid == 0) {
-    for (int s = 0; s < LS; ++s) { mbar_init(full + s, LOADERS / 2); mbar_init(lo_empty + s, 1); }
+    for (int s = 0; s < LS; ++s) { mbar_init(full + s, LOADERS / 64); mbar_init(lo_empty + s, 1); }
     for (int s = 0; s < RS; ++s) mbar_init(raw_empty + s, 1);
     mbar_init(blk_full, 1);
     mbar_init(blk_done, 4);
@@ -275,13 +275,20 @@ vg_gemm3(const __grid_constant__ Args g) {
       }
       for (int t = set; t < n_stages; t += 2) {
         cp_wait<1>();                                        // this thread's pieces of stage t have landed
-        if (t >= LS) mbar_wait(lo_empty + t % LS, (uint32_t)(t / LS - 1) & 1u);
+        if (t >= LS) {                                       // one lane polls, the warp follows (128 spinning threads cost
+          if (lane == 0) mbar_wait(lo_empty + t % LS, (uint32_t)(t / LS - 1) & 1u);  // shared-memory bandwidth the MMAs need)
+          __syncwarp();
+        }
         split(t);
         fence_async_smem();
-        mbar_arrive(full + t % LS);
+        __syncwarp();                                        // one arrival per warp: 128 arrivals per stage on one shared-memory
+        if (lane == 0) mbar_arrive(full + t % LS);           // word serialise (they were most of the loaders' per-stage chain)
         const int tn = t + 4;                                // into the slot this set's stage t - 2 used
         if (tn < n_stages) {
-          if (tn >= RS) mbar_wait(raw_empty + tn % RS, (uint32_t)(tn / RS - 1) & 1u);
+          if (tn >= RS) {
+            if (lane == 0) mbar_wait(raw_empty + tn % RS, (uint32_t)(tn / RS - 1) & 1u);
+            __syncwarp();
+          }
           issue(tn);
         }
         cp_commit();

@@ -2,7 +2,7 @@
 //
 // Same program, same row layout ([row][sample], samples contiguous) as the fused interpreter
 // (vm.cuh), but the rows of a *chunk* of C samples live in the caller's workspace in global memory
-// (C up to 131072 samples: wide enough to fill the GPU with the per-sample kernels) and every matrix product is its own tiled
+// (C up to 262144 samples: wide enough to fill the GPU with the per-sample kernels) and every matrix product is its own tiled
 // FP32 kernel:
 //   vg_linear  out[j][s] = act(b[j] + sum_i W[i][j] in[i][s])        M = samples, N = outputs, K = inputs
 //   vg_dw      grad[i][j] += sum_s in[i][s] g[j][s]  (+ bias row)      contraction over the samples
@@ -309,7 +309,7 @@ namespace {
 inline size_t a256(size_t n) { return (n + 255) & ~(size_t)255; }
 // chunk width target: SURJ_B200_CHUNK at load time, surj_set_chunk_samples() afterwards (tests run multi-chunk cases
 // at oracle-sized batches with it; 0 restores the default)
-constexpr int64_t kDefaultChunk = 131072;
+constexpr int64_t kDefaultChunk = 262144;
 // fused conditioner + spline kernel (vm_fused.cuh) on / off: SURJ_B200_FUSION at load time, surj_set_wide_fusion() afterwards
 std::atomic<int> g_fusion{[] { const char* e = getenv("SURJ_B200_FUSION"); return e ? atoi(e) : 1; }()};
 std::atomic<int64_t> g_chunk_target{[] { const char* e = getenv("SURJ_B200_CHUNK"); return e ? atoll(e) : kDefaultChunk; }()};

@@ -47,7 +47,7 @@ def test_scaled_configs_multi_chunk(name, mode):
 
 @pytest.mark.parametrize("name,batch", [("cfg4", (1 << 18) + 77), ("cfg5", (1 << 18) + 77)])
 def test_large_batch_properties(name, batch):
-  """Default chunk width (131072): batch 2^18 + 77 = two full chunks and a ragged third."""
+  """Default chunk width (262144): batch 2^18 + 77 = one full chunk and a ragged second (tests above cover three chunks)."""
   pm, pparams, om, oparams, y64, x64 = parity.build_pair(name, 8, 0, 0.15)
   dev = torch.device("cuda:0")
   params = parity.to_device(pparams, dev)
