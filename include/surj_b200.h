@@ -142,6 +142,9 @@ int32_t surj_plan_is_fused(const SurjPlan* plan);
 int32_t surj_plan_dim_out(const SurjPlan* plan);
 /* number of kernels one fwd / one bwd call launches (for launch accounting) */
 int32_t surj_plan_launches(const SurjPlan* plan, int32_t backward);
+/* MaskedAutoregressive layers whose sampling direction (masked_autoregressive.py:63-71, D MADE passes upstream) the
+ * per-op executor runs as ONE incremental kernel (0 on the fused executors, which keep the D passes) */
+int32_t surj_plan_sampling_recursions(const SurjPlan* plan);
 
 /* bytes of device scratch a call with batch B needs (backward != 0 for the VJP) */
 size_t surj_plan_workspace_bytes(const SurjPlan* plan, int64_t batch, int32_t backward);

@@ -124,6 +124,7 @@ _SIGNATURES = {
   "surj_bench_tf32_peak": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]),
   "surj_profile_begin": (C.c_int, []),
   "surj_profile_end": (C.c_int64, [C.c_char_p, C.c_int64]),
+  "surj_plan_sampling_recursions": (C.c_int32, [C.c_void_p]),
   "surj_set_chunk_samples": (C.c_int64, [C.c_int64]),
   "surj_set_wide_fusion": (C.c_int32, [C.c_int32]),
   "surj_last_error": (C.c_char_p, []),

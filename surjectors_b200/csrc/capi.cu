@@ -420,6 +420,11 @@ extern "C" size_t surj_plan_workspace_bytes(const SurjPlan* plan, int64_t batch,
   return vm_global_workspace_bytes(plan->vmp, batch, backward != 0);
 }
 
+extern "C" int32_t surj_plan_sampling_recursions(const SurjPlan* plan) {
+  if (!plan || !plan->vmp || plan->exec != 3) return 0;
+  return vm_global_maf_groups(plan->vmp);
+}
+
 extern "C" int32_t surj_plan_launches(const SurjPlan* plan, int32_t backward) {
   if (!plan) return 0;
   if (plan->exec == 1 || plan->exec == 2 || plan->exec == 4) return backward ? 2 : 1;

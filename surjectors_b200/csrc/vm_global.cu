@@ -23,6 +23,7 @@
 #include "vm_tc.cuh"
 #include "vm_fused.cuh"
 #include "vm_gemm3.cuh"
+#include "vm_maf.cuh"
 
 // ---- per-kernel timing (surj_profile_begin / surj_profile_end): every launch of the executor bracketed by events
 namespace prof {
@@ -442,8 +443,101 @@ const VmTcInfo& tc_info(const VmPlan* v, int prog) {
       i = e;
     }
   }
+
+  // ---- MaskedAutoregressive sampling: OP_ZERO + D identical copies of [GATHER?, LINEAR.., AFFINE] -> one recursion kernel
+  t.maf.clear();
+  t.maf_at.assign(ops.size(), -1);
+  if (fusion_now) {
+    for (size_t i = 0; i + 2 < ops.size(); ++i) {
+      if (ops[i].code != vm::OP_ZERO) continue;
+      const int D = ops[i].a[1];
+      size_t e = i + 1;
+      while (e < ops.size() && (ops[e].code == vm::OP_GATHER || ops[e].code == vm::OP_LINEAR)) ++e;
+      static const bool maf_dbg = getenv("SURJ_B200_MAF_DBG") != nullptr;
+      if (e >= ops.size() || ops[e].code != vm::OP_AFFINE) { if (maf_dbg) fprintf(stderr, "[maf] op %zu: block does not end in AFFINE (code %d)\n", i, e < ops.size() ? ops[e].code : -1); continue; }
+      const size_t len = e - i;  // ops per copy
+      if (D < 2 || D > vmaf::MAX_D || i + 1 + (size_t)D * len > ops.size()) { if (maf_dbg) fprintf(stderr, "[maf] op %zu: D %d len %zu size %zu\n", i, D, len, ops.size()); continue; }
+      bool same = true;
+      for (int c = 1; c < D && same; ++c)
+        for (size_t q = 0; q < len && same; ++q) {
+          vm::Op a = ops[i + 1 + q], b = ops[i + 1 + (size_t)c * len + q];
+          if (a.code == vm::OP_AFFINE) a.a[9] = b.a[9] = 0;  // only the last copy adds its log-det
+          same = std::memcmp(&a, &b, sizeof a) == 0;
+        }
+      if (!same) { if (maf_dbg) fprintf(stderr, "[maf] op %zu: copies differ\n", i); continue; }
+      const vm::Op& af = ops[e];
+      const vm::Op& af_last = ops[i + (size_t)D * len];
+      // affine inner on interleaved thetas, y rows = what the first LINEAR reads, all D dims in order
+      bool ok = af.a[2] == D && af.a[5] == 2 && af.a[7] == 2 && af.a[6] == af.a[4] + 1 && ops[i].a[0] == af.a[1] &&
+                (af.a[8] == vm::INNER_AFFINE || af.a[8] == vm::INNER_AFFINE_INV);
+      for (int k = 0; k < D && ok; ++k) ok = v->itab[af.a[3] + k] == k;
+      vmaf::Desc d{};
+      VmMafGroup g;
+      g.first = (int)i; g.last = (int)(i + (size_t)D * len);
+      std::vector<const vm::Op*> lin;
+      for (size_t q = i + 1; q < e; ++q) {
+        if (ops[q].code == vm::OP_GATHER) { if (g.gather >= 0) ok = false; g.gather = (int)q; }
+        else lin.push_back(&ops[q]);
+      }
+      ok = ok && !lin.empty() && lin[0]->a[0] == af.a[1] && lin[0]->a[1] == D;
+      if (!ok) { if (maf_dbg) fprintf(stderr, "[maf] op %zu: affine / first layer shape\n", i); continue; }
+      d.z_row = af.a[0]; d.y_row = af.a[1]; d.D = D; d.P = 2; d.inner = af.a[8]; d.skip_lp = af_last.a[9];
+      size_t li = 0;
+      int ctx_out_row = -1;
+      std::vector<const vm::Op*> masked;
+      masked.push_back(lin[li++]);
+      d.act0 = masked[0]->a[7];
+      if (li < lin.size() && lin[li]->a[8] == 1) {  // context Linear accumulated onto layer 0's pre-activation
+        const vm::Op& c = *lin[li++];
+        ok = ok && g.gather >= 0 && c.a[0] == ops[g.gather].a[0] && c.a[12] == masked[0]->a[12] && masked[0]->a[7] == vm::ACT_IDENTITY;
+        ctx_out_row = c.a[4];
+        d.has_ctx = 1; d.cc_row = c.a[0]; d.ctx_dim = c.a[1]; d.ctx_wt_off = c.a[10]; d.ctx_ldt = c.a[11]; d.ctx_b_off = c.a[6];
+        d.act0 = c.a[7];
+      } else if (g.gather >= 0) ok = false;
+      for (; li < lin.size(); ++li) masked.push_back(lin[li]);
+      ok = ok && (int)masked.size() >= 1 && (int)masked.size() <= vmaf::MAX_LAYERS && masked.back()->a[4] == af.a[4] &&
+           masked.back()->a[12] == 2 * D && masked.back()->a[7] == vm::ACT_IDENTITY;
+      if (!ok) { if (maf_dbg) fprintf(stderr, "[maf] op %zu: layer structure (ctx / output layer)\n", i); continue; }
+      d.n_layers = (int)masked.size();
+      // ready step of every hidden unit, read off the staged masks (primary [in][out] copies)
+      std::vector<std::vector<int>> rdy(masked.size());
+      for (size_t l = 0; l < masked.size() && ok; ++l) {
+        const vm::Op& o = *masked[l];
+        d.wt_off[l] = o.a[10]; d.ldt[l] = o.a[11]; d.b_off[l] = o.a[6]; d.n_in[l] = o.a[1]; d.n_out[l] = o.a[12]; d.act[l] = o.a[7];
+        // (with a context Linear, layer 0's activations are what THAT op writes: it accumulates onto layer 0's pre-activations)
+        if (l > 0) ok = ok && o.a[0] == ((l == 1 && d.has_ctx) ? ctx_out_row : masked[l - 1]->a[4]) && o.a[1] == masked[l - 1]->a[12] && o.a[8] == 0;
+        rdy[l].assign(o.a[12], 0);
+        for (int in = 0; in < o.a[1]; ++in)
+          for (int out = 0; out < o.a[12]; ++out)
+            if (v->stage[(size_t)o.a[2] + (size_t)in * o.a[3] + out] != vm::STAGE_ZERO)
+              rdy[l][out] = std::max(rdy[l][out], l == 0 ? in + 1 : rdy[l - 1][in]);
+        if (l + 1 < masked.size()) {
+          ok = ok && o.a[12] <= 65535;
+          for (int j = 1; j < o.a[12] && ok; ++j) ok = rdy[l][j] >= rdy[l][j - 1];  // contiguous ranges per step
+          for (int st = 0; st <= D && ok; ++st) {
+            int c = 0;
+            while (c < o.a[12] && rdy[l][c] <= st) ++c;
+            d.cum[l][st] = (unsigned short)c;
+          }
+        } else {
+          for (int dd = 0; dd < D && ok; ++dd) ok = rdy[l][2 * dd] <= dd && rdy[l][2 * dd + 1] <= dd;  // autoregressive
+        }
+      }
+      if (!ok) { if (maf_dbg) fprintf(stderr, "[maf] op %zu: layer chain / ready ranges not contiguous / not autoregressive\n", i); continue; }
+      g.wbuf = (vmaf::max_step_floats(d) + 31) & ~31;
+      g.smem = ((size_t)vmaf::warp_floats(d) * vmaf::WARPS + 2 * (size_t)g.wbuf) * 4;
+      if (g.smem > 200 * 1024) { if (maf_dbg) fprintf(stderr, "[maf] op %zu: %zu bytes of shared memory\n", i, g.smem); continue; }
+      g.desc.resize(sizeof d);
+      std::memcpy(g.desc.data(), &d, sizeof d);
+      t.maf_at[i] = (int)t.maf.size();
+      t.maf.push_back(g);
+      i = (size_t)g.last;
+    }
+  }
   std::vector<char> in_group(ops.size(), 0);
   for (const VmFusedGroup& g : t.fused)
+    for (int q = g.first; q <= g.last; ++q) in_group[q] = 1;
+  for (const VmMafGroup& g : t.maf)
     for (int q = g.first; q <= g.last; ++q) in_group[q] = 1;
   std::map<int, long long> seen;
   t.w_off.assign(ops.size(), -1);
@@ -492,6 +586,12 @@ Carve carve(const VmPlan* v, void* ws, int C, int prog) {
 }
 }  // namespace
 
+// number of MaskedAutoregressive sampling recursions the per-op executor runs as ONE kernel each (host-side query)
+int vm_global_maf_groups(const VmPlan* v) {
+  if (v->ops_gen.empty()) return 0;
+  return (int)tc_info(v, VM_PROG_GEN).maf.size();
+}
+
 extern "C" int32_t surj_set_wide_fusion(int32_t on) {
   const int prev = g_fusion.load();
   g_fusion.store(on ? 1 : 0);
@@ -519,6 +619,7 @@ int vm_global_launches(const VmPlan* v, int64_t B, bool backward) {
   bool in_run = false;
   for (size_t pc = 0; pc < ops.size(); ++pc) {
     if (tci.fused_at[pc] >= 0) { ++per_chunk; in_run = false; pc = (size_t)tci.fused[tci.fused_at[pc]].last; continue; }
+    if (tci.maf_at[pc] >= 0) { per_chunk += 1 + (tci.maf[tci.maf_at[pc]].gather >= 0 ? 1 : 0); in_run = false; pc = (size_t)tci.maf[tci.maf_at[pc]].last; continue; }
     const vm::Op& op = ops[pc];
     const bool mat = op.code == vm::OP_LINEAR || op.code == vm::OP_LINEAR_DW;
     if (mat) { ++per_chunk; in_run = false; }
@@ -628,6 +729,25 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
     bool first = true;
     while (pc < ops.size()) {
       const vm::Op& op = ops[pc];
+      if (tci.maf_at[pc] >= 0) {  // MaskedAutoregressive sampling: the D-pass recursion as ONE incremental kernel
+        const VmMafGroup& g = tci.maf[tci.maf_at[pc]];
+        vmaf::Desc d;
+        std::memcpy(&d, g.desc.data(), sizeof d);
+        if (g.gather >= 0) {
+          prof::Scope ps(st, prof::ELEM, 0.0);
+          vm::vg_elem<<<cols / 128, 128, 0, st>>>(d_ops + g.gather, 1, 0, io, k.rows, C, base, B, P.itab, k.scal, k.scal_g, k.loss);
+        }
+        static const bool attr = [] {
+          cudaFuncSetAttribute(vmaf::vg_maf_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          return true;
+        }();
+        (void)attr;
+        const int grid = std::min((cols + vmaf::WARPS - 1) / vmaf::WARPS, v->n_sm * 2);
+        prof::Scope ps(st, prof::LINEAR_SIMT, 0.0);
+        vmaf::vg_maf_forward<<<grid, 32 * vmaf::WARPS, g.smem, st>>>(d, k.rows, C, cols, k.par, g.wbuf);
+        pc = (size_t)g.last + 1;
+        continue;
+      }
       if (tci.fused_at[pc] >= 0) {  // conditioner MLP + spline (or its VJP) of one coupling layer in ONE launch
         const VmFusedGroup& g = tci.fused[tci.fused_at[pc]];
         const vm::Op& sp = ops[g.last];
@@ -743,7 +863,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
         ++pc;
       } else {
         size_t e = pc;
-        while (e < ops.size() && ops[e].code != vm::OP_LINEAR && ops[e].code != vm::OP_LINEAR_DW) ++e;
+        while (e < ops.size() && ops[e].code != vm::OP_LINEAR && ops[e].code != vm::OP_LINEAR_DW && (e == pc || tci.maf_at[e] < 0)) ++e;
         prof::Scope ps(st, prof::ELEM, 0.0);
         vm::vg_elem<<<cols / 128, 128, 0, st>>>(d_ops + pc, (int)(e - pc), first ? 1 : 0, io, k.rows, C, base, B, P.itab,
                                               k.scal, k.scal_g, k.loss);

@@ -24,8 +24,18 @@ struct VmImgMat {  // mirrors vmf::ImgMat (kept POD here so that this header sta
   int wt_off, ldt, n_rows, n_k, rows_per_block, n_blocks, N, k_pad, scale_slot;
   long long img_off;
 };
+// MaskedAutoregressive sampling recursion recognised in a program (vm_maf.cuh): ops [first, last] = OP_ZERO + D copies of the
+// MADE block; desc = the kernel's descriptor (vmaf::Desc) as bytes so that this header stays CUDA-free
+struct VmMafGroup {
+  int first = 0, last = 0, gather = -1;  // gather: index of the context GATHER op of the first copy (-1: unconditional MADE)
+  std::vector<unsigned char> desc;
+  size_t smem = 0;
+  int wbuf = 0;                          // floats of one weight staging buffer (the largest step's rows)
+};
 struct VmTcInfo {
   bool ready = false;
+  std::vector<VmMafGroup> maf;             // by first op
+  std::vector<int> maf_at;                 // per op: index into `maf` if a recursion starts there, else -1
   int fusion_flag = -1;                    // the fusion setting `fused` was computed under
   std::vector<VmFusedGroup> fused;         // fused conditioner + spline groups, by first op
   std::vector<int> fused_at;               // per op: index into `fused` if a group starts there, else -1
@@ -67,6 +77,7 @@ struct VmPlan {
 enum { VM_PROG_FWD = 0, VM_PROG_BWD = 1, VM_PROG_GEN = 2 };
 size_t vm_global_workspace_bytes(const VmPlan* v, int64_t B, bool backward);
 int vm_global_launches(const VmPlan* v, int64_t B, bool backward);
+int vm_global_maf_groups(const VmPlan* v);
 int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const float* y, const float* x,
                   const float* params, const float* g_lp, float g_scale, const float* g_z, float* z_out, float* lp_out,
                   float* g_y, float* g_x, float* g_params, float* loss_out, void* ws, size_t ws_bytes, int64_t B,

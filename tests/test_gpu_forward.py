@@ -200,3 +200,47 @@ def test_sample_api_on_cfg2():
   assert tuple(y.shape) == (1000, 20) and tuple(lp.shape) == (1000,) and bool(torch.isfinite(y).all())
   y2 = m.apply(params, 11, method="sample", sample_shape=(1000,))
   assert torch.equal(y, y2)  # same rng -> same draws
+
+
+@pytest.mark.parametrize("conditional", [False, True])
+@pytest.mark.parametrize("dim,hidden", [(24, [48, 48]), (64, [96]), (7, [16, 16, 16])])
+def test_maf_sampling_recursion_kernel_matches_the_unrolled_passes(dim, hidden, conditional):
+  """masked_autoregressive.py:63-71 runs D MADE passes; the per-op executor runs ONE incremental pass (csrc/vm_maf.cuh).
+  Same parameters, same latents: the recursion kernel against the D unrolled passes (fusion off), and a round trip
+  through the inverse direction."""
+  from surjectors_b200 import _abi
+
+  def _inv_affine(params):  # the examples' Inverse(ScalarAffine) variant (examples/autoregressive_inference_surjection.py:35-37)
+    means, log_scales = unstack(params, -1)
+    return distrax.Inverse(distrax.ScalarAffine(means, jnp.exp(log_scales)))
+
+  def build():
+    return sj.Chain([sj.AffineMaskedAutoregressive(MADE(dim, hidden, 2)), sj.Permutation(np.arange(dim)[::-1].copy(), 1),
+                     sj.MaskedAutoregressive(MADE(dim, hidden, 2), _inv_affine)])
+
+  inv = hk.transform(lambda **kw: build().inverse_and_likelihood_contribution(**kw))
+  fwd = hk.transform(lambda **kw: build().forward_and_likelihood_contribution(**kw))
+  B = 300
+  g = torch.Generator().manual_seed(dim)
+  z = torch.randn((B, dim), generator=g).to(DEV)
+  kw = dict(x=torch.randn((B, 5), generator=g).to(DEV)) if conditional else {}
+  lib = _abi.lib()
+  res = {}
+  with execution_mode("layered"):
+    params = fwd.init(0, z=z, **kw)
+    _randomize(params, 13, scale=0.7 if dim < 32 else 0.25)  # (a 64-step recursion amplifies: keep the scales of order one)
+    for on in (0, 1):
+      prev = lib.surj_set_wide_fusion(on)
+      try:
+        res[on] = fwd.apply(params, None, z=z, **kw)
+      finally:
+        lib.surj_set_wide_fusion(prev)
+    y1, fl1 = res[1]
+    z_back, lc = inv.apply(params, None, y=y1, **kw)
+  y0, fl0 = res[0]
+  assert torch.isfinite(y1).all()
+  tol = 2e-5 if dim < 32 else 2e-4  # two float32 evaluation orders of a D-step recursion
+  assert torch.allclose(y1, y0, rtol=tol, atol=tol), float((y1 - y0).abs().max())
+  assert torch.allclose(fl1, fl0, rtol=tol, atol=tol), float((fl1 - fl0).abs().max())
+  assert torch.allclose(z_back, z, rtol=10 * tol, atol=10 * tol), float((z_back - z).abs().max())
+  assert torch.allclose(fl1, -lc, rtol=10 * tol, atol=10 * tol)

@@ -244,3 +244,26 @@ def test_forced_executors_refuse_chains_they_do_not_cover():
     else:
       with pytest.raises(NotImplementedError):  # SURJ_E_UNSUPPORTED, as the reference raises for unsupported structure
         _runtime.Plan(spec, mode=_runtime.MODES[mode])
+
+
+def test_sampling_recursion_is_recognised():
+  """masked_autoregressive.py:63-71 (D MADE passes upstream): the per-op executor must run every affine MaskedAutoregressive
+  of a chain as ONE incremental kernel (csrc/vm_maf.cuh) -- a host-side property of the compiled plan."""
+  import numpy as np
+
+  import surjectors_b200 as sj
+  from surjectors_b200 import _abi, _runtime
+  from surjectors_b200.nn import MADE
+
+  for dim, hidden, dx in ((128, [512, 512], 16), (24, [48], 0), (6, [16, 16, 16], 3)):
+    def build():
+      return sj.Chain([sj.AffineMaskedAutoregressive(MADE(dim, hidden, 2)), sj.Permutation(np.arange(dim)[::-1].copy(), 1),
+                       sj.AffineMaskedAutoregressive(MADE(dim, hidden, 2))])
+
+    fwd = hk.transform(lambda **kw: build().forward_and_likelihood_contribution(**kw))
+    kw = dict(z=torch.zeros(2, dim))
+    if dx:
+      kw["x"] = torch.zeros(2, dx)
+    traced, _ = fwd.trace(**kw)
+    plan = _runtime.Plan(traced[0], _runtime.BASE_NONE, _abi.MODE_LAYERED)
+    assert _abi.lib().surj_plan_sampling_recursions(plan._h) == 2, (dim, hidden, dx)
