@@ -651,12 +651,12 @@ def run_b200(args):
     cpu = {"value": c["samples_per_s"], "unit": "samples/s", "cores": c["cores"], "kind": "port", "sample": cpu_sample_text(c, B)}
 
   if ctx.rank == 0:
-    cfgd = config_dict(main_cfg, B, ctx.world, r["params"])
+    cfgd = config_dict(main_cfg, B, ctx.world, None)  # identical in both arms (the driver compares them)
     line = {
       "metric": "train_samples_per_sec", "value": r["train_samples_per_sec"], "unit": "samples/s", "n_gpus": ctx.world,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
-      "run": {"l2": r["l2"], "cuda_graph": r["cuda_graph"], "executor": r["executor"], "train_steps_per_sec": 1e3 / r["ms_per_step"],
+      "run": {"params": r["params"], "l2": r["l2"], "cuda_graph": r["cuda_graph"], "executor": r["executor"], "train_steps_per_sec": 1e3 / r["ms_per_step"],
               "needed_flops_per_sample_fwd": r["needed_flops_per_sample_fwd"], "dense_flops_per_sample_fwd": r["dense_flops_per_sample_fwd"]},
       "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "cpu_baseline": cpu,
       "log_prob": r["log_prob"], "final_loss": r["final_loss"],

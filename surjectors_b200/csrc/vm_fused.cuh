@@ -454,11 +454,15 @@ __device__ __forceinline__ void tm_fwd(const SplineTm& s, float v, bool forward,
 // VJP: cotangent of theta -> rows [th_row + c][sample] (p = &rows[th_row * C + sample]); returns the cotangent of v.
 // After tm_locate<KEEP> the accumulator holds exp(theta - max) for widths / heights: the sweep is a multiply per entry.
 template <int NCH, bool FULL>
-__device__ __forceinline__ float tm_bwd(const SplineTm& s, float* __restrict__ p, size_t C, float v, bool forward, float g_out, float g_ld) {
+__device__ __forceinline__ float tm_bwd(const SplineTm& s, float* __restrict__ p, size_t C, float v, bool forward, float g_out, float g_ld,
+                                        long long* tt) {
+  const long long c0 = tt ? clock64() : 0;
   vm::RqsBin b;
   tm_locate<NCH, FULL, true>(s, v, forward, b);
+  const long long c1 = tt ? clock64() : 0;
   vm::RqsGrad G;
   vm::rqs_bwd_core(b, s.K, s.lo, s.hi, v, forward, g_out, g_ld, G);
+  const long long c2 = tt ? clock64() : 0;
   const int K = s.K;
   const bool tail = G.ks >= 0;
   const int kb = b.bin;
@@ -489,6 +493,7 @@ __device__ __forceinline__ float tm_bwd(const SplineTm& s, float* __restrict__ p
     else { if (k == kb) g = G.g_u0; if (k == kb + 1) g = G.g_u1; }
     p[(size_t)(2 * K + k) * C] = g;
   }
+  if (tt) { tt[0] += c1 - c0; tt[1] += c2 - c1; tt[2] += clock64() - c2; }
   return G.g_v;
 }
 
@@ -548,6 +553,7 @@ vg_fused_rqs(const __grid_constant__ Desc d, float* __restrict__ rows, int C, in
   const bool rec = dbg != nullptr && blockIdx.x == 0;
   const long long t_start = rec ? clock64() : 0;
   long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
+  long long tt[3] = {0, 0, 0};
 #define TIMED(acc, stmt) do { if (rec) { const long long t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while (0)
 
   if (warp == 0) {
@@ -767,7 +773,7 @@ vg_fused_rqs(const __grid_constant__ Desc d, float* __restrict__ rows, int C, in
           float* gp = rows + (size_t)(d.th_row + j * d.P) * C + col;
           float g_v = 0.0f;
           with_chunks(d.K_bins, [&](auto nch, auto full) {
-            g_v = tm_bwd<decltype(nch)::value, decltype(full)::value>(th, gp, (size_t)C, v, forward_spline, g_out, g_lp);
+            g_v = tm_bwd<decltype(nch)::value, decltype(full)::value>(th, gp, (size_t)C, v, forward_spline, g_out, g_lp, rec ? tt : nullptr);
           });
           rows[(size_t)(d.gin_row + dim) * C + col] = g_v;
         }
@@ -796,6 +802,9 @@ vg_fused_rqs(const __grid_constant__ Desc d, float* __restrict__ rows, int C, in
     atomicAdd((unsigned long long*)dbg + 7, (unsigned long long)w2);
     atomicAdd((unsigned long long*)dbg + 8, (unsigned long long)w3);
     atomicAdd((unsigned long long*)dbg + 9, (unsigned long long)w4);
+    atomicAdd((unsigned long long*)dbg + 14, (unsigned long long)tt[0]);
+    atomicAdd((unsigned long long*)dbg + 15, (unsigned long long)tt[1]);
+    atomicAdd((unsigned long long*)dbg + 16, (unsigned long long)tt[2]);
   }
 #undef TIMED
   tc_fence_before();

@@ -273,26 +273,37 @@ vg_gemm3(const __grid_constant__ Args g) {
         if (t < n_stages) issue(t);
         cp_commit();
       }
+      const bool lrec = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+      long long lt[5] = {0, 0, 0, 0, 0};
       for (int t = set; t < n_stages; t += 2) {
+        long long c0 = lrec ? clock64() : 0;
         cp_wait<1>();                                        // this thread's pieces of stage t have landed
+        long long c1 = lrec ? clock64() : 0;
         if (t >= LS) {                                       // one lane polls, the warp follows (128 spinning threads cost
           if (lane == 0) mbar_wait(lo_empty + t % LS, (uint32_t)(t / LS - 1) & 1u);  // shared-memory bandwidth the MMAs need)
           __syncwarp();
         }
+        long long c2 = lrec ? clock64() : 0;
         split(t);
         fence_async_smem();
         __syncwarp();                                        // one arrival per warp: 128 arrivals per stage on one shared-memory
         if (lane == 0) mbar_arrive(full + t % LS);           // word serialise (they were most of the loaders' per-stage chain)
+        long long c3 = lrec ? clock64() : 0;
         const int tn = t + 4;                                // into the slot this set's stage t - 2 used
         if (tn < n_stages) {
           if (tn >= RS) {
             if (lane == 0) mbar_wait(raw_empty + tn % RS, (uint32_t)(tn / RS - 1) & 1u);
             __syncwarp();
           }
+          long long c4 = lrec ? clock64() : 0;
           issue(tn);
+          if (lrec) { lt[3] += c4 - c3; lt[4] += clock64() - c4; }
         }
         cp_commit();
+        if (lrec) { lt[0] += c1 - c0; lt[1] += c2 - c1; lt[2] += c3 - c2; }
       }
+      if (lrec)
+        for (int q = 0; q < 5; ++q) atomicAdd((unsigned long long*)g.dbg + 17 + q, (unsigned long long)lt[q]);
     } else if (MODE == 1 && blockIdx.x == 0 && g.gb_off >= 0) {
       // masked tile that still owes the bias gradient of its columns: plain column sums
       for (int j = warp; j < n_valid; j += 8) {

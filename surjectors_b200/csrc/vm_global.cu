@@ -51,14 +51,14 @@ static long long* fused_dbg_buffer() {
   static long long* buf = [] {
     long long* p = nullptr;
     const char* e = getenv("SURJ_B200_FUSED_DBG");
-    if (e && atoi(e)) { cudaMalloc(&p, 16 * sizeof(long long)); cudaMemset(p, 0, 16 * sizeof(long long)); }
+    if (e && atoi(e)) { cudaMalloc(&p, 24 * sizeof(long long)); cudaMemset(p, 0, 24 * sizeof(long long)); }
     return p;
   }();
   return buf;
 }
 
 extern "C" int surj_profile_begin(void) {
-  if (long long* d = fused_dbg_buffer()) cudaMemset(d, 0, 16 * sizeof(long long));
+  if (long long* d = fused_dbg_buffer()) cudaMemset(d, 0, 24 * sizeof(long long));
   for (auto& r : prof::g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   prof::g_recs.clear();
   prof::g_on = true;
@@ -69,11 +69,13 @@ extern "C" int64_t surj_profile_end(char* out, int64_t out_bytes) {
   prof::g_on = false;
   cudaDeviceSynchronize();
   if (long long* d = fused_dbg_buffer()) {
-    long long h[16];
+    long long h[24];
     cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[fused dbg, CTA 0, cycles] producer waits free slot %lld | MMA waits weights %lld, accumulator %lld, operand %lld | "
             "epilogue warp 2: waits accumulator %lld, hidden phases %lld, bias staging %lld, input load %lld, spline %lld | CTA total %lld\n", h[0], h[1], h[2], h[3], h[4], h[6], h[7], h[9], h[8], h[5]);
+    fprintf(stderr, "[fused dbg, VJP of one dim, epilogue warp 2, cycles] locate %lld, scalar core %lld, cotangent sweep %lld\n", h[14], h[15], h[16]);
     fprintf(stderr, "[gemm3 dbg, CTA 0 MMA issuer, cycles] waits split stage %lld, waits block drain %lld, total %lld, stages %lld\n", h[10], h[11], h[12], h[13]);
+    fprintf(stderr, "[gemm3 dbg, CTA 0 loader thread 0, cycles] waits data %lld, waits lo slot %lld, split + fence + arrive %lld, waits raw slot %lld, issue %lld\n", h[17], h[18], h[19], h[20], h[21]);
   }
   double ms[prof::N_KINDS] = {0}, fl[prof::N_KINDS] = {0};
   long long n[prof::N_KINDS] = {0};
