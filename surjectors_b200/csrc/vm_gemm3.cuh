@@ -19,6 +19,7 @@
 // MMA costs the same 140-cycle floor, tools/ubench/f16_probe.cu), and 2 x 256 columns are all of tensor memory.
 // Warp roles (416 threads): 0..7 load + split, 8 issues the MMAs, 9..12 drain / epilogue (TMEM lanes 32 * (warp % 4)).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -54,6 +55,22 @@ __device__ __forceinline__ uint32_t soff(int r, int k) {  // byte offset of elem
 }
 __device__ __forceinline__ uint64_t desc16(uint32_t saddr) {  // LBO 128 B, SBO = KQ core matrices of 4 k per 8-row group
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | ((uint64_t)(KQ * 8) << 32) | (1ull << 46);
+}
+// TMA-fed variant (TMA = true): one elected thread of a 14th warp issues tensor loads -- LINEAR_DW and the weight operand of
+// LINEAR: box {16 k, rows} with the 64-byte swizzle (K-major, SBO 512 B, k step of 8 = +32 B); LINEAR's activations,
+// sample-major in memory: four boxes {32 samples, 16 k} with the 128-byte swizzle on 32-byte atoms, the shared-memory form
+// tcgen05 wants for an MN-major 32-bit operand (layout code 1, LBO 2048 B = next 32 samples, SBO 512 B = next 4 k, k step
+// of 8 = +1024 B, instruction-descriptor bit 15) -- both validated on exact integer data by tools/ubench/tma_probe.cu.
+// The eight loader warps then only split (lo = x - trunc(x) is elementwise: piece i of the stage's bytes -> piece i of the
+// lo stage, whatever the swizzle).  Why: the cp.async path is bound by the LDGSTS issue rate (12 cp.async per thread and
+// owned stage take 1.7 .. 2.4k cycles; the data itself arrives in time -- in-kernel counters, profiles/r2_summary.md).
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint64_t desc_sw(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint64_t layout) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void cp16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -118,9 +135,10 @@ struct Args {
 };
 
 // MODE 0: LINEAR, grid (sample tiles, ceil(n_out / 256)).   MODE 1: LINEAR_DW, grid (ceil(n_in / 128), ceil(n_out / 256), slabs).
-template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1)
-vg_gemm3(const __grid_constant__ Args g) {
+// TMA: tensor-load producer warp (THREADS + 32 threads, map_a / map_b from make_maps below); else cp.async loaders, maps unused.
+template <int MODE, bool TMA>
+__global__ void __launch_bounds__(TMA ? THREADS + 32 : THREADS, 1)
+vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* raw = base;                                  // [RS][A | B]
@@ -131,7 +149,8 @@ vg_gemm3(const __grid_constant__ Args g) {
   uint64_t* raw_empty = lo_empty + LS;  // [RS] MMA commit
   uint64_t* blk_full = raw_empty + RS;  // [1]  MMA commit: a block's accumulator is complete
   uint64_t* blk_done = blk_full + 1;    // [1]  4 arrivals: the block has been added to the master
-  uint32_t* tmem_slot = (uint32_t*)(blk_done + 1);
+  uint64_t* raw_full = blk_done + 1;    // [RS] TMA only: the stage's bytes have landed
+  uint32_t* tmem_slot = (uint32_t*)(raw_full + RS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- this CTA's problem
@@ -167,7 +186,7 @@ vg_gemm3(const __grid_constant__ Args g) {
 
   if (tid == 0) {
     for (int s = 0; s < LS; ++s) { mbar_init(full + s, LOADERS / 64); mbar_init(lo_empty + s, 1); }
-    for (int s = 0; s < RS; ++s) mbar_init(raw_empty + s, 1);
+    for (int s = 0; s < RS; ++s) { mbar_init(raw_empty + s, 1); mbar_init(raw_full + s, 1); }
     mbar_init(blk_full, 1);
     mbar_init(blk_done, 4);
   }
@@ -183,7 +202,83 @@ vg_gemm3(const __grid_constant__ Args g) {
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_work = tmem, t_master = tmem + TN;
 
-  if (warp < 8) {
+  if (TMA && warp < 8) {
+    // ------------------------------------------------------------------ splitters behind the tensor loads
+    // two sets of four warps take the stages in turn; thread ts of the set splits pieces ts + 128 e of the stage's 1536
+    // (consecutive lanes, consecutive 16 bytes: conflict-free; the first 512 pieces are A, row of a B piece = (piece - 512) / 4)
+    const int set = warp >> 2, ts = tid & 127;
+    constexpr int PA = A_BYTES / 16 / 128, PB = B_BYTES / 16 / 128;  // 4, 8
+    float bsum[PB];
+#pragma unroll
+    for (int e = 0; e < PB; ++e) bsum[e] = 0.0f;
+    auto low = [](const float4& x) {
+      float4 l;
+      l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+      l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+      l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+      l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+      return l;
+    };
+    if (!skip_tile) {
+      for (int t = set; t < n_stages; t += 2) {
+        if (lane == 0) {
+          mbar_wait(raw_full + t % RS, (uint32_t)(t / RS) & 1u);
+          if (t >= LS) mbar_wait(lo_empty + t % LS, (uint32_t)(t / LS - 1) & 1u);
+        }
+        __syncwarp();
+        const unsigned char* sr = raw + (size_t)(t % RS) * STAGE_BYTES;
+        unsigned char* sl = lo + (size_t)(t % LS) * STAGE_BYTES;
+        float4 x[PA + PB];
+#pragma unroll
+        for (int e = 0; e < PA + PB; ++e)
+          if (e < PA || (ts >> 2) + 32 * (e - PA) < n_tile) x[e] = *reinterpret_cast<const float4*>(sr + 16 * (ts + 128 * e));
+#pragma unroll
+        for (int e = 0; e < PA + PB; ++e)
+          if (e < PA || (ts >> 2) + 32 * (e - PA) < n_tile) {
+            *reinterpret_cast<float4*>(sl + 16 * (ts + 128 * e)) = low(x[e]);
+            if (MODE == 1 && e >= PA) bsum[e - PA] += (x[e].x + x[e].y) + (x[e].z + x[e].w);
+          }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + t % LS);
+      }
+      if (MODE == 1 && blockIdx.x == 0 && g.gb_off >= 0) {  // bias gradient: the four pieces of a g row sit in four consecutive lanes
+#pragma unroll
+        for (int e = 0; e < PB; ++e) {
+          float a = bsum[e];
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          const int r = (ts >> 2) + 32 * e;
+          if ((ts & 3) == 0 && r < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r, a);
+        }
+      }
+    } else if (MODE == 1 && blockIdx.x == 0 && g.gb_off >= 0) {
+      for (int j = warp; j < n_valid; j += 8) {
+        const float* gr = g.b_base + (long long)(n0 + j) * g.b_pitch;
+        float a = 0.0f;
+        for (int s = k_begin + lane; s < k_end; s += 32) a += gr[s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) atomicAdd(g.grad + g.gb_off + n0 + j, a);
+      }
+    }
+  } else if (TMA && warp == 13) {
+    if (lane == 0 && !skip_tile) {  // ------------------------------------------------------ tensor-load producer
+      for (int t = 0; t < n_stages; ++t) {
+        if (t >= RS) mbar_wait(raw_empty + t % RS, (uint32_t)(t / RS - 1) & 1u);
+        const int k0 = k_begin + t * KS;
+        const uint32_t sa = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sb = sa + A_BYTES;
+        vmtc::mbar_expect_tx(raw_full + t % RS, STAGE_BYTES);
+        if (MODE == 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_2d(sa + 2048u * c, &map_a, m0 + 32 * c, k0, raw_full + t % RS);
+        } else {
+          tma_2d(sa, &map_a, k0, m0, raw_full + t % RS);
+        }
+        tma_2d(sb, &map_b, k0, n0, raw_full + t % RS);
+      }
+    }
+  } else if (warp < 8) {
     // ------------------------------------------------------------------ loaders: cp.async, then split what they loaded
     // A tile 128 x 16 floats = 512 pieces of 16 B (2 per thread); B tile 256 x 16 = 1024 pieces (4 per thread);
     // piece q -> row q / 4, k quarter q % 4 (K-major sources).  LINEAR's A is sample-major: element-wise 4-byte copies,
@@ -201,70 +296,92 @@ vg_gemm3(const __grid_constant__ Args g) {
     float bsum[PB];  // DW: running sums of this thread's g rows (bias gradient)
 #pragma unroll
     for (int e = 0; e < PB; ++e) bsum[e] = 0.0f;
+    // Per-thread addressing, computed once: piece e of this thread is row r0 + 32 e, k quarter kq (piece_of(ts + 128 e)), so
+    // shared-memory offsets are so0 + 2048 e and global addresses advance by 32 rows per piece and KS floats per stage.
+    // (Computing row / quarter / validity / 64-bit address per piece and stage cost the loaders 1.7k cycles per owned
+    // stage -- as much as the split -- and the MMA issuer waited for them 57 % of its time.)
+    const int r0 = (ts & 7) | ((ts >> 5) << 3), kq0 = (ts >> 3) & 3;
+    const uint32_t so0 = soff(r0, 4 * kq0);
+    const float* pb0 = g.b_base + (long long)(n0 + r0) * g.b_pitch + k_begin + 4 * kq0;
+    const long long pb_step = 32 * g.b_pitch;
+    const float* pa0;      // MODE 1: like pb0.  MODE 0: row (lane / 8) of the stage, sample m0 + 32 wq + lane % 8
+    long long pa_step;     // MODE 1: 32 rows.   MODE 0: 4 rows (one k quarter)
+    uint32_t sa0 = 0;      // MODE 0: soff of this lane's element in copy 0
+    if (MODE == 0) {
+      pa0 = g.a_base + (long long)(k_begin + (lane >> 3)) * g.a_pitch + m0 + 32 * wq + (lane & 7);
+      pa_step = 4 * g.a_pitch;
+      sa0 = soff(32 * wq + (lane & 7), lane >> 3);
+    } else {
+      pa0 = g.a_base + (long long)(m0 + r0) * g.a_pitch + k_begin + 4 * kq0;
+      pa_step = 32 * g.a_pitch;
+    }
     auto issue = [&](int t) {
       const int k0 = k_begin + t * KS;
       const uint32_t sa = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sb = sa + A_BYTES;
+      const bool whole = k0 + KS <= k_end;       // every k of the stage exists (all stages but a ragged last one)
       if (MODE == 0) {  // sample-major source, element-wise copies: a warp instruction moves 8 samples x the 4 k of one quarter
-                        // (32 distinct banks; 4 sectors of 32 B in memory); warp w of the set, step e -> sample group (16 w + e) / 4, quarter (16 w + e) % 4
+                        // (32 distinct banks; 4 sectors of 32 B in memory); step e -> samples 32 wq + 8 (e / 4) + lane % 8, k = 4 (e % 4) + lane / 8
+        const float* pa = pa0 + (long long)(t * KS) * g.a_pitch;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const int c = 16 * wq + e, smp = ((c >> 2) << 3) | (lane & 7), k = 4 * (c & 3) + (lane >> 3);
-          const bool ok = k0 + k < k_end;
-          cp4(sa + soff(smp, k), g.a_base + (long long)(ok ? k0 + k : 0) * g.a_pitch + m0 + smp, ok ? 4 : 0);
+          const bool ok = whole || k0 + 4 * (e & 3) + (lane >> 3) < k_end;
+          // soff(smp + 8 (e / 4), k + 4 (e % 4)) = sa0 + (e / 4) * KQ * 128 + (e % 4) * 128
+          cp4(sa + sa0 + (uint32_t)((e >> 2) * (KQ * 128) + (e & 3) * 128), ok ? pa + (e & 3) * pa_step + 8 * (e >> 2) : g.a_base, ok ? 4 : 0);
         }
       } else {
+        const float* pa = pa0 + t * KS;
 #pragma unroll
         for (int e = 0; e < PA; ++e) {
-          int r, kq;
-          piece_of(ts + 128 * e, r, kq);
-          const int kk = k0 + 4 * kq;
-          const int nb = (r < m_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
-          cp16(sa + soff(r, 4 * kq), g.a_base + (long long)(nb ? m0 + r : 0) * g.a_pitch + (nb ? kk : 0), nb);
+          const int kk = k0 + 4 * kq0;
+          const int nb = r0 + 32 * e < m_valid ? (whole ? 16 : (kk < k_end ? min(16, 4 * (k_end - kk)) : 0)) : 0;
+          cp16(sa + so0 + 2048u * e, nb ? pa + e * pa_step : g.a_base, nb);
         }
       }
+      const float* pb = pb0 + t * KS;
 #pragma unroll
       for (int e = 0; e < PB; ++e) {
-        int r, kq;
-        piece_of(ts + 128 * e, r, kq);
-        const int kk = k0 + 4 * kq;
-        const int nb = (r < n_valid && kk < k_end) ? min(16, 4 * (k_end - kk)) : 0;
-        if (r < n_tile) cp16(sb + soff(r, 4 * kq), g.b_base + (long long)(nb ? n0 + r : 0) * g.b_pitch + (nb ? kk : 0), nb);
+        const int kk = k0 + 4 * kq0;
+        const int nb = r0 + 32 * e < n_valid ? (whole ? 16 : (kk < k_end ? min(16, 4 * (k_end - kk)) : 0)) : 0;
+        if (r0 + 32 * e < n_tile) cp16(sb + so0 + 2048u * e, nb ? pb + e * pb_step : g.b_base, nb);
       }
     };
+    // all of a stage's pieces are read before any lo piece is written: the loads are independent (the compiler cannot
+    // prove the two rings disjoint and would otherwise order every load behind the previous piece's store)
     auto split = [&](int t) {
       unsigned char* sr = raw + (size_t)(t % RS) * STAGE_BYTES;
       unsigned char* sl = lo + (size_t)(t % LS) * STAGE_BYTES;
-      auto one = [&](uint32_t off, float* sum) {
-        const float4 x = *reinterpret_cast<const float4*>(sr + off);
+      auto low = [](const float4& x) {
         float4 l;
         l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
         l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
         l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
         l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-        *reinterpret_cast<float4*>(sl + off) = l;
-        if (sum != nullptr) *sum += (x.x + x.y) + (x.z + x.w);
+        return l;
       };
-      if (MODE == 0) {  // the warp splits the 128 pieces it copied (the 4 k of a piece came from 4 lanes: warp-level sync first)
-        __syncwarp();
+      float4 xa[PA], xb[PB];
+      uint32_t oa[PA];
+      if (MODE == 0) __syncwarp();  // the 4 k of a piece came from 4 lanes of this warp
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int pi = lane + 32 * j, c = 16 * wq + (pi >> 3);
-          one(soff(((c >> 2) << 3) | (pi & 7), 4 * (c & 3)), nullptr);
+      for (int e = 0; e < PA; ++e) {
+        if (MODE == 0) {  // the warp splits the 128 pieces it copied
+          const int pi = lane + 32 * e, c = 16 * wq + (pi >> 3);
+          oa[e] = soff(((c >> 2) << 3) | (pi & 7), 4 * (c & 3));
+        } else {
+          oa[e] = so0 + 2048u * e;
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < PA; ++e) {
-          int r, kq;
-          piece_of(ts + 128 * e, r, kq);
-          one(soff(r, 4 * kq), nullptr);
-        }
+        xa[e] = *reinterpret_cast<const float4*>(sr + oa[e]);
       }
 #pragma unroll
-      for (int e = 0; e < PB; ++e) {
-        int r, kq;
-        piece_of(ts + 128 * e, r, kq);
-        if (r < n_tile) one(A_BYTES + soff(r, 4 * kq), MODE == 1 ? &bsum[e] : nullptr);
-      }
+      for (int e = 0; e < PB; ++e)
+        if (r0 + 32 * e < n_tile) xb[e] = *reinterpret_cast<const float4*>(sr + A_BYTES + so0 + 2048u * e);
+#pragma unroll
+      for (int e = 0; e < PA; ++e) *reinterpret_cast<float4*>(sl + oa[e]) = low(xa[e]);
+#pragma unroll
+      for (int e = 0; e < PB; ++e)
+        if (r0 + 32 * e < n_tile) {
+          *reinterpret_cast<float4*>(sl + A_BYTES + so0 + 2048u * e) = low(xb[e]);
+          if (MODE == 1) bsum[e] += (xb[e].x + xb[e].y) + (xb[e].z + xb[e].w);
+        }
     };
     if (!skip_tile) {
       // per set: the stage being split plus two in flight; the refill of a slot is issued at the END of an iteration (it
@@ -321,9 +438,7 @@ vg_gemm3(const __grid_constant__ Args g) {
         float a = bsum[e];
         a += __shfl_xor_sync(0xffffffffu, a, 8);
         a += __shfl_xor_sync(0xffffffffu, a, 16);
-        int r, kq;
-        piece_of(ts + 128 * e, r, kq);
-        if (kq == 0 && r < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r, a);
+        if (kq0 == 0 && r0 + 32 * e < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r0 + 32 * e, a);
       }
     }
   } else if (warp == 8) {
@@ -331,7 +446,8 @@ vg_gemm3(const __grid_constant__ Args g) {
       const bool rec = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
       long long w_full = 0, w_blk = 0;
       const long long t_start = rec ? clock64() : 0;
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TMA && MODE == 0) ? (1u << 15) : 0u) | ((uint32_t)(n_tile >> 3) << 17) |
+                             ((uint32_t)(TM >> 4) << 24);
       for (int t = 0; t < n_stages; ++t) {
         const int blk = t / BLK;
         long long c0 = rec ? clock64() : 0;
@@ -341,13 +457,22 @@ vg_gemm3(const __grid_constant__ Args g) {
         if (rec) { w_blk += c1 - c0; w_full += clock64() - c1; }
         tc_fence_after();
         const uint32_t sr = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sl = smem_u32(lo + (size_t)(t % LS) * STAGE_BYTES);
-        const uint64_t da_hi = desc16(sr), db_hi = desc16(sr + A_BYTES), da_lo = desc16(sl), db_lo = desc16(sl + A_BYTES);
+        uint64_t da_hi, db_hi, da_lo, db_lo, adv_a, adv_b;  // adv: start-address step (in 16 B) of a k step of 8
+        if (TMA) {
+          mbar_wait(raw_full + t % RS, (uint32_t)(t / RS) & 1u);  // (already complete: the splitters waited for it)
+          if (MODE == 0) { da_hi = desc_sw(sr, 2048, 512, 1); da_lo = desc_sw(sl, 2048, 512, 1); adv_a = 1024 >> 4; }
+          else { da_hi = desc_sw(sr, 16, 512, 4); da_lo = desc_sw(sl, 16, 512, 4); adv_a = 32 >> 4; }
+          db_hi = desc_sw(sr + A_BYTES, 16, 512, 4); db_lo = desc_sw(sl + A_BYTES, 16, 512, 4); adv_b = 32 >> 4;
+        } else {
+          da_hi = desc16(sr); db_hi = desc16(sr + A_BYTES); da_lo = desc16(sl); db_lo = desc16(sl + A_BYTES);
+          adv_a = adv_b = 16;  // two core matrices = 256 B
+        }
 #pragma unroll
         for (int ks = 0; ks < KS / 8; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * 16);  // two core matrices = 256 B
-          vmtc::mma_tf32(t_work, da_lo + adv, db_hi + adv, idesc, (t % BLK == 0 && ks == 0) ? 0u : 1u);
-          vmtc::mma_tf32(t_work, da_hi + adv, db_lo + adv, idesc, 1u);
-          vmtc::mma_tf32(t_work, da_hi + adv, db_hi + adv, idesc, 1u);
+          const uint64_t aa = adv_a * ks, ab = adv_b * ks;
+          vmtc::mma_tf32(t_work, da_lo + aa, db_hi + ab, idesc, (t % BLK == 0 && ks == 0) ? 0u : 1u);
+          vmtc::mma_tf32(t_work, da_hi + aa, db_lo + ab, idesc, 1u);
+          vmtc::mma_tf32(t_work, da_hi + aa, db_hi + ab, idesc, 1u);
         }
         umma_commit(raw_empty + t % RS);
         umma_commit(lo_empty + t % LS);
@@ -360,7 +485,7 @@ vg_gemm3(const __grid_constant__ Args g) {
         atomicAdd((unsigned long long*)g.dbg + 13, (unsigned long long)n_stages);
       }
     }
-  } else if (!skip_tile) {
+  } else if (warp <= 12 && !skip_tile) {
     // ------------------------------------------------------------------------ drain warps 9..12, then the epilogue
     const int quarter = warp & 3;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -426,6 +551,38 @@ vg_gemm3(const __grid_constant__ Args g) {
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+// ---- host: tensor maps of the TMA-fed variant (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TmapEncodeFn tmap_encode_fn() {
+  static TmapEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (TmapEncodeFn)f;
+  }();
+  return fn;
+}
+// float32 matrix [outer][inner] with row pitch `pitch` floats; false if TMA cannot describe it (alignment) -> caller uses cp.async
+inline bool make_tmap(CUtensorMap* m, const float* base, long long inner, long long outer, long long pitch, int box_inner, int box_outer,
+                      CUtensorMapSwizzle sw) {
+  TmapEncodeFn enc = tmap_encode_fn();
+  if (!enc || ((uintptr_t)base & 15u) || (pitch & 3) || inner <= 0 || outer <= 0) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer}, strides[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer}, es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// maps of a launch: MODE 0 (LINEAR): A = in rows [K][samples] read in boxes {32 samples, 16 k}; MODE 1 (LINEAR_DW): A = in rows
+// [n_in][samples] in boxes {16 samples, 128 rows}.  B: rows [b_rows][K] in boxes {16 k, 256 rows}.  Out-of-bounds rows / k read as zeros.
+inline bool make_maps(int mode, const Args& a, long long samples, CUtensorMap* ma, CUtensorMap* mb) {
+  if (mode == 0)
+    return make_tmap(ma, a.a_base, samples, a.a_rows, a.a_pitch, 32, KS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+           make_tmap(mb, a.b_base, a.K, a.b_rows, a.b_pitch, KS, TN, CU_TENSOR_MAP_SWIZZLE_64B);
+  return make_tmap(ma, a.a_base, a.K, a.a_rows, a.a_pitch, KS, TM, CU_TENSOR_MAP_SWIZZLE_64B) &&
+         make_tmap(mb, a.b_base, a.K, a.b_rows, a.b_pitch, KS, TN, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 }  // namespace vmg

@@ -648,14 +648,18 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   }();
   const bool use_tc_lin = tc_mode == 1 || tc_mode == 2 || tc_mode == 5 || tc_mode == 6, use_tc_dw = tc_mode == 1 || tc_mode == 3 || tc_mode == 5;
   const bool gemm3 = tc_mode == 6;
+  // operands of the gemm3 kernels by TMA tensor loads (bit 0: LINEAR_DW, bit 1: LINEAR); 0: cp.async loaders
+  static const int gemm3_tma = [] { const char* e = getenv("SURJ_B200_GEMM3_TMA"); return e ? atoi(e) : 3; }();
   static const bool use_tc = [] {
     const bool on = true;
     if (on) {
       cudaFuncSetAttribute(vmtc::vg_linear_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::PIPE_SMEM);
       cudaFuncSetAttribute(vmtc::vg_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::SMEM_BYTES);
       cudaFuncSetAttribute(vmtc::vg_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmtc::SMEM_BYTES);
-      cudaFuncSetAttribute(vmg::vg_gemm3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
-      cudaFuncSetAttribute(vmg::vg_gemm3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
+      cudaFuncSetAttribute(vmg::vg_gemm3<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
+      cudaFuncSetAttribute(vmg::vg_gemm3<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
+      cudaFuncSetAttribute(vmg::vg_gemm3<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
+      cudaFuncSetAttribute(vmg::vg_gemm3<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
     }
     return on;
   }();
@@ -802,7 +806,9 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           a.dbg = fused_dbg_buffer();
           dim3 grid(cols / vmg::TM, (op.a[5] + vmg::TN - 1) / vmg::TN);
           prof::Scope ps(st, prof::LINEAR_TC, fl);
-          vmg::vg_gemm3<0><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a);
+          CUtensorMap ma{}, mb{};
+          if ((gemm3_tma & 2) && vmg::make_maps(0, a, cols, &ma, &mb)) vmg::vg_gemm3<0, true><<<grid, vmg::THREADS + 32, vmg::SMEM_BYTES, st>>>(a, ma, mb);
+          else vmg::vg_gemm3<0, false><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
         } else if (pipe && tci.w_off[pc] >= 0) {  // tcgen05 3xTF32, TMA-fed pipeline on pre-tiled operands
           const int nkb = (op.a[1] + vmtc::PBK - 1) / vmtc::PBK;
           { prof::Scope ps(st, prof::TILE, 0.0);
@@ -845,7 +851,9 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           a.k_slab = ((cols + best_slabs - 1) / best_slabs + 255) / 256 * 256;
           dim3 grid(ti, tj, (cols + a.k_slab - 1) / a.k_slab);
           prof::Scope ps(st, prof::DW_TC, fl);
-          vmg::vg_gemm3<1><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a);
+          CUtensorMap ma{}, mb{};
+          if ((gemm3_tma & 1) && vmg::make_maps(1, a, cols, &ma, &mb)) vmg::vg_gemm3<1, true><<<grid, vmg::THREADS + 32, vmg::SMEM_BYTES, st>>>(a, ma, mb);
+          else vmg::vg_gemm3<1, false><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
         } else if (use_tc && use_tc_dw && NA >= 32 && NG >= 32) {
           // sample slabs sized so the grid fills the machine about twice (2 CTAs per SM x 148 SMs x 2)
           // (the bias gradient comes out of staging the g operand, so the tile rows cover the n_in real inputs only)
