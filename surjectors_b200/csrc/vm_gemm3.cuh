@@ -47,6 +47,15 @@ constexpr int RS = 6, LS = 2;                  // raw / lo ring depths
 constexpr int KQ = KS / 4;                     // 16-byte pieces per row and stage
 constexpr int A_BYTES = TM * KS * 4, B_BYTES = TN * KS * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int LOADERS = 256, THREADS = 416;
+// TMA-fed variant.  A stage holds a raw slot from the tensor load's issue until its MMAs complete (load latency L ~ 1800
+// cycles + split S + MMAs E) and a lo slot from the split's start until then (S + E); S is ~870 cycles of LDS / STS for 12
+// pieces per thread plus ~700 .. 1400 for the proxy fence (fence.proxy.async after the lo pieces are written), E ~ 930
+// (six 128 x 256 x 8 MMAs).  Throughput is min(raw slots / (L + S + E), lo slots / (S + E), sets / S, 1 / E) -- measured
+// (cfg4 train step, cycles per stage on CTA 0 / weight-gradient ms / input-gradient ms):
+//   raw 6, lo 2, 2 sets of 4 warps: 1750 / 145 / 154     raw 4, lo 4, 4 sets of 2 warps: 1840 / 154 / 158
+//   raw 5, lo 3, 2 sets of 4 warps: 1310 / 112 / 130     raw 5, lo 3, 3 sets of 4 warps (576 threads, drain spills): 1660 / 138 / 160
+constexpr int TRS = 5, TLS = 3, TSETS = 2, TSW = 8;   // raw / lo ring depths, splitter sets, splitter warps
+constexpr int TMA_THREADS = (TSW + 6) * 32;            // + MMA issuer, four drain warps, tensor-load producer
 constexpr size_t SMEM_BYTES = 1024 + (size_t)(RS + LS) * STAGE_BYTES + 256;
 static_assert(SMEM_BYTES <= 227 * 1024, "rings exceed the shared memory of an SM");
 
@@ -134,23 +143,114 @@ struct Args {
                                                        // [11] for the drain of a block, [12] its total cycles
 };
 
+// remote arrive on the barrier at the same shared-memory offset in CTA 0 of the cluster (the pair's leader)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(0));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope (arrivals from the peer CTA)
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_C;\n\t"
+      "bra WAIT_LOOP_C;\n\t"
+      "DONE_C:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// drain warps 9..12: add every finished block of the work accumulator into the master, then the epilogue from tensor memory.
+// PAIR: blk_done lives in the leader CTA (8 arrivals: four warps of each CTA).
+template <int MODE, bool PAIR>
+__device__ __forceinline__ void drain_epilogue(const Args& g, int warp, int lane, int n_blocks, int n_stages, int n_tile, int n_valid, int n0,
+                                               int m0, uint32_t t_work, uint32_t t_master, uint64_t* blk_full, uint64_t* blk_done) {
+  const int quarter = warp & 3;
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+  for (int blk = 0; blk < n_blocks; ++blk) {
+    mbar_wait(blk_full, (uint32_t)blk & 1u);
+    tc_fence_after();
+    if (n_blocks > 1) {  // master (+)= work, round-to-nearest
+      for (int c0 = 0; c0 < n_tile; c0 += 32) {
+        uint32_t w[32], m[32];
+        tm_ld32(t_work + lane_addr + (uint32_t)c0, w);
+        if (blk > 0) tm_ld32(t_master + lane_addr + (uint32_t)c0, m);
+        tm_ld_wait();
+        if (blk > 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) + __uint_as_float(m[i]));
+        }
+        tm_st32(t_master + lane_addr + (uint32_t)c0, w);
+      }
+      tm_st_wait();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) { if (PAIR) mbar_arrive_leader(blk_done); else mbar_arrive(blk_done); }
+  }
+  const uint32_t t_acc = (n_blocks > 1 ? t_master : t_work) + lane_addr;
+  tc_fence_after();
+  if (MODE == 0) {
+    const long long col = (long long)m0 + quarter * 32 + lane;  // this thread's sample
+    const int acc_row = g.pre_row >= 0 ? g.pre_row : g.out_row;
+    const int n_write = min(TN, g.n_out - n0);                   // padded outputs of this tile
+    vm::with_act(g.act, [&](auto tag) {
+      constexpr int ACT = decltype(tag)::value;
+      for (int c0 = 0; c0 < n_write; c0 += 32) {
+        uint32_t w[32];
+        if (n_stages > 0) { tm_ld32(t_acc + (uint32_t)c0, w); tm_ld_wait(); }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int j = n0 + c0 + i;
+          if (c0 + i < n_write) {
+            float x = (n_stages > 0 ? __uint_as_float(w[i]) : 0.0f) + (g.b_off >= 0 ? __ldg(g.par + g.b_off + j) : 0.0f);
+            if (g.accumulate) x += g.rows[(long long)(acc_row + j) * g.C + col];
+            if (g.pre_row >= 0) g.rows[(long long)(g.pre_row + j) * g.C + col] = x;
+            g.rows[(long long)(g.out_row + j) * g.C + col] = vm::act_fwd(ACT, x);
+          }
+        }
+      }
+    });
+  } else if (n_stages > 0) {
+    const int i = m0 + quarter * 32 + lane;  // TMEM lane = input feature
+    for (int c0 = 0; c0 < n_valid; c0 += 32) {
+      uint32_t w[32];
+      tm_ld32(t_acc + (uint32_t)c0, w);
+      tm_ld_wait();
+      if (i < g.n_in) {
+        float* dst = g.grad + g.w_off + (long long)i * g.ld + n0 + c0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (c0 + q < n_valid) atomicAdd(dst + q, __uint_as_float(w[q]));
+      }
+    }
+  }
+}
+
 // MODE 0: LINEAR, grid (sample tiles, ceil(n_out / 256)).   MODE 1: LINEAR_DW, grid (ceil(n_in / 128), ceil(n_out / 256), slabs).
 // TMA: tensor-load producer warp (THREADS + 32 threads, map_a / map_b from make_maps below); else cp.async loaders, maps unused.
 template <int MODE, bool TMA>
-__global__ void __launch_bounds__(TMA ? THREADS + 32 : THREADS, 1)
+__global__ void __launch_bounds__(TMA ? TMA_THREADS : THREADS, 1)
 vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
+  constexpr int RSx = TMA ? TRS : RS, LSx = TMA ? TLS : LS;   // ring depths of this variant
+  constexpr int NSW = TMA ? TSW : 8;                          // warps 0 .. NSW-1 load / split, NSW issues the MMAs, NSW+1 .. NSW+4 drain, NSW+5 produces
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* raw = base;                                  // [RS][A | B]
-  unsigned char* lo = base + (size_t)RS * STAGE_BYTES;        // [LS][A | B]
-  uint64_t* bars = (uint64_t*)(lo + (size_t)LS * STAGE_BYTES);
-  uint64_t* full = bars;             // [LS]  4 arrivals (the warps of the set that owns the stage): split and visible
-  uint64_t* lo_empty = full + LS;    // [LS]  MMA commit
-  uint64_t* raw_empty = lo_empty + LS;  // [RS] MMA commit
-  uint64_t* blk_full = raw_empty + RS;  // [1]  MMA commit: a block's accumulator is complete
+  unsigned char* raw = base;                                  // [RSx][A | B]
+  unsigned char* lo = base + (size_t)RSx * STAGE_BYTES;        // [LSx][A | B]
+  uint64_t* bars = (uint64_t*)(lo + (size_t)LSx * STAGE_BYTES);
+  uint64_t* full = bars;             // [LSx]  4 arrivals (the warps of the set that owns the stage): split and visible
+  uint64_t* lo_empty = full + LSx;    // [LSx]  MMA commit
+  uint64_t* raw_empty = lo_empty + LSx;  // [RSx] MMA commit
+  uint64_t* blk_full = raw_empty + RSx;  // [1]  MMA commit: a block's accumulator is complete
   uint64_t* blk_done = blk_full + 1;    // [1]  4 arrivals: the block has been added to the master
-  uint64_t* raw_full = blk_done + 1;    // [RS] TMA only: the stage's bytes have landed
-  uint32_t* tmem_slot = (uint32_t*)(raw_full + RS);
+  uint64_t* raw_full = blk_done + 1;    // [RSx] TMA only: the stage's bytes have landed
+  uint32_t* tmem_slot = (uint32_t*)(raw_full + RSx);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- this CTA's problem
@@ -185,8 +285,8 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
   }
 
   if (tid == 0) {
-    for (int s = 0; s < LS; ++s) { mbar_init(full + s, LOADERS / 64); mbar_init(lo_empty + s, 1); }
-    for (int s = 0; s < RS; ++s) { mbar_init(raw_empty + s, 1); mbar_init(raw_full + s, 1); }
+    for (int s = 0; s < LSx; ++s) { mbar_init(full + s, TMA ? TSW / TSETS : LOADERS / 64); mbar_init(lo_empty + s, 1); }
+    for (int s = 0; s < RSx; ++s) { mbar_init(raw_empty + s, 1); mbar_init(raw_full + s, 1); }
     mbar_init(blk_full, 1);
     mbar_init(blk_done, 4);
   }
@@ -202,12 +302,13 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_work = tmem, t_master = tmem + TN;
 
-  if (TMA && warp < 8) {
+  if (TMA && warp < NSW) {
     // ------------------------------------------------------------------ splitters behind the tensor loads
-    // two sets of four warps take the stages in turn; thread ts of the set splits pieces ts + 128 e of the stage's 1536
+    // TSETS sets of warps take the stages in turn; thread ts of the set splits pieces ts + SETT e of the stage's 1536
     // (consecutive lanes, consecutive 16 bytes: conflict-free; the first 512 pieces are A, row of a B piece = (piece - 512) / 4)
-    const int set = warp >> 2, ts = tid & 127;
-    constexpr int PA = A_BYTES / 16 / 128, PB = B_BYTES / 16 / 128;  // 4, 8
+    constexpr int SETT = TSW * 32 / TSETS;             // threads of a set
+    constexpr int PA = A_BYTES / 16 / SETT, PB = B_BYTES / 16 / SETT, HALF = (PA + PB) / 2;
+    const int set = warp / (TSW / TSETS), ts = tid % SETT;
     float bsum[PB];
 #pragma unroll
     for (int e = 0; e < PB; ++e) bsum[e] = 0.0f;
@@ -220,40 +321,56 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
       return l;
     };
     if (!skip_tile) {
-      for (int t = set; t < n_stages; t += 2) {
+      const bool lrec = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+      long long lt[4] = {0, 0, 0, 0};
+      for (int t = set; t < n_stages; t += TSETS) {
+        long long c0 = lrec ? clock64() : 0, c1 = 0;
         if (lane == 0) {
-          mbar_wait(raw_full + t % RS, (uint32_t)(t / RS) & 1u);
-          if (t >= LS) mbar_wait(lo_empty + t % LS, (uint32_t)(t / LS - 1) & 1u);
+          mbar_wait(raw_full + t % RSx, (uint32_t)(t / RSx) & 1u);
+          c1 = lrec ? clock64() : 0;
+          if (t >= LSx) mbar_wait(lo_empty + t % LSx, (uint32_t)(t / LSx - 1) & 1u);
         }
         __syncwarp();
-        const unsigned char* sr = raw + (size_t)(t % RS) * STAGE_BYTES;
-        unsigned char* sl = lo + (size_t)(t % LS) * STAGE_BYTES;
-        float4 x[PA + PB];
+        long long c2 = lrec ? clock64() : 0;
+        const unsigned char* sr = raw + (size_t)(t % RSx) * STAGE_BYTES;
+        unsigned char* sl = lo + (size_t)(t % LSx) * STAGE_BYTES;
 #pragma unroll
-        for (int e = 0; e < PA + PB; ++e)
-          if (e < PA || (ts >> 2) + 32 * (e - PA) < n_tile) x[e] = *reinterpret_cast<const float4*>(sr + 16 * (ts + 128 * e));
+        for (int h = 0; h < 2; ++h) {  // two batches: all loads of a batch before its stores (independent loads), 48 registers
+          float4 x[HALF];
 #pragma unroll
-        for (int e = 0; e < PA + PB; ++e)
-          if (e < PA || (ts >> 2) + 32 * (e - PA) < n_tile) {
-            *reinterpret_cast<float4*>(sl + 16 * (ts + 128 * e)) = low(x[e]);
-            if (MODE == 1 && e >= PA) bsum[e - PA] += (x[e].x + x[e].y) + (x[e].z + x[e].w);
+          for (int q = 0; q < HALF; ++q) {
+            const int e = h * HALF + q;
+            if (e < PA || (ts >> 2) + (SETT / 4) * (e - PA) < n_tile) x[q] = *reinterpret_cast<const float4*>(sr + 16 * (ts + SETT * e));
           }
+#pragma unroll
+          for (int q = 0; q < HALF; ++q) {
+            const int e = h * HALF + q;
+            if (e < PA || (ts >> 2) + (SETT / 4) * (e - PA) < n_tile) {
+              *reinterpret_cast<float4*>(sl + 16 * (ts + SETT * e)) = low(x[q]);
+              if (MODE == 1 && e >= PA) bsum[e - PA] += (x[q].x + x[q].y) + (x[q].z + x[q].w);
+            }
+          }
+        }
+        long long c3 = lrec ? clock64() : 0;
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(full + t % LS);
+        if (lane == 0) mbar_arrive(full + t % LSx);
+        if (lrec) { lt[0] += c1 - c0; lt[1] += c2 - c1; lt[2] += c3 - c2; lt[3] += clock64() - c3; }
       }
+      if (lrec)
+        for (int q = 0; q < 4; ++q) atomicAdd((unsigned long long*)g.dbg + 17 + q, (unsigned long long)lt[q]);
       if (MODE == 1 && blockIdx.x == 0 && g.gb_off >= 0) {  // bias gradient: the four pieces of a g row sit in four consecutive lanes
 #pragma unroll
         for (int e = 0; e < PB; ++e) {
           float a = bsum[e];
           a += __shfl_xor_sync(0xffffffffu, a, 1);
           a += __shfl_xor_sync(0xffffffffu, a, 2);
-          const int r = (ts >> 2) + 32 * e;
+          const int r = (ts >> 2) + (SETT / 4) * e;
           if ((ts & 3) == 0 && r < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r, a);
         }
       }
     } else if (MODE == 1 && blockIdx.x == 0 && g.gb_off >= 0) {
-      for (int j = warp; j < n_valid; j += 8) {
+      for (int j = warp; j < n_valid; j += NSW) {
         const float* gr = g.b_base + (long long)(n0 + j) * g.b_pitch;
         float a = 0.0f;
         for (int s = k_begin + lane; s < k_end; s += 32) a += gr[s];
@@ -262,20 +379,20 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
         if (lane == 0) atomicAdd(g.grad + g.gb_off + n0 + j, a);
       }
     }
-  } else if (TMA && warp == 13) {
+  } else if (TMA && warp == NSW + 5) {
     if (lane == 0 && !skip_tile) {  // ------------------------------------------------------ tensor-load producer
       for (int t = 0; t < n_stages; ++t) {
-        if (t >= RS) mbar_wait(raw_empty + t % RS, (uint32_t)(t / RS - 1) & 1u);
+        if (t >= RSx) mbar_wait(raw_empty + t % RSx, (uint32_t)(t / RSx - 1) & 1u);
         const int k0 = k_begin + t * KS;
-        const uint32_t sa = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sb = sa + A_BYTES;
-        vmtc::mbar_expect_tx(raw_full + t % RS, STAGE_BYTES);
+        const uint32_t sa = smem_u32(raw + (size_t)(t % RSx) * STAGE_BYTES), sb = sa + A_BYTES;
+        vmtc::mbar_expect_tx(raw_full + t % RSx, STAGE_BYTES);
         if (MODE == 0) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tma_2d(sa + 2048u * c, &map_a, m0 + 32 * c, k0, raw_full + t % RS);
+          for (int c = 0; c < 4; ++c) tma_2d(sa + 2048u * c, &map_a, m0 + 32 * c, k0, raw_full + t % RSx);
         } else {
-          tma_2d(sa, &map_a, k0, m0, raw_full + t % RS);
+          tma_2d(sa, &map_a, k0, m0, raw_full + t % RSx);
         }
-        tma_2d(sb, &map_b, k0, n0, raw_full + t % RS);
+        tma_2d(sb, &map_b, k0, n0, raw_full + t % RSx);
       }
     }
   } else if (warp < 8) {
@@ -441,7 +558,7 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
         if (kq0 == 0 && r0 + 32 * e < n_valid) atomicAdd(g.grad + g.gb_off + n0 + r0 + 32 * e, a);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == NSW) {
     if (lane == 0 && !skip_tile) {  // ---------------------------------------------------- MMA issuer
       const bool rec = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
       long long w_full = 0, w_blk = 0;
@@ -453,13 +570,13 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
         long long c0 = rec ? clock64() : 0;
         if (t % BLK == 0 && blk > 0) mbar_wait(blk_done, (uint32_t)(blk - 1) & 1u);  // the work accumulator has been drained
         long long c1 = rec ? clock64() : 0;
-        mbar_wait(full + t % LS, (uint32_t)(t / LS) & 1u);
+        mbar_wait(full + t % LSx, (uint32_t)(t / LSx) & 1u);
         if (rec) { w_blk += c1 - c0; w_full += clock64() - c1; }
         tc_fence_after();
-        const uint32_t sr = smem_u32(raw + (size_t)(t % RS) * STAGE_BYTES), sl = smem_u32(lo + (size_t)(t % LS) * STAGE_BYTES);
+        const uint32_t sr = smem_u32(raw + (size_t)(t % RSx) * STAGE_BYTES), sl = smem_u32(lo + (size_t)(t % LSx) * STAGE_BYTES);
         uint64_t da_hi, db_hi, da_lo, db_lo, adv_a, adv_b;  // adv: start-address step (in 16 B) of a k step of 8
         if (TMA) {
-          mbar_wait(raw_full + t % RS, (uint32_t)(t / RS) & 1u);  // (already complete: the splitters waited for it)
+          mbar_wait(raw_full + t % RSx, (uint32_t)(t / RSx) & 1u);  // (already complete: the splitters waited for it)
           if (MODE == 0) { da_hi = desc_sw(sr, 2048, 512, 1); da_lo = desc_sw(sl, 2048, 512, 1); adv_a = 1024 >> 4; }
           else { da_hi = desc_sw(sr, 16, 512, 4); da_lo = desc_sw(sl, 16, 512, 4); adv_a = 32 >> 4; }
           db_hi = desc_sw(sr + A_BYTES, 16, 512, 4); db_lo = desc_sw(sl + A_BYTES, 16, 512, 4); adv_b = 32 >> 4;
@@ -474,8 +591,8 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
           vmtc::mma_tf32(t_work, da_hi + aa, db_lo + ab, idesc, 1u);
           vmtc::mma_tf32(t_work, da_hi + aa, db_hi + ab, idesc, 1u);
         }
-        umma_commit(raw_empty + t % RS);
-        umma_commit(lo_empty + t % LS);
+        umma_commit(raw_empty + t % RSx);
+        umma_commit(lo_empty + t % LSx);
         if (t % BLK == BLK - 1 || t == n_stages - 1) umma_commit(blk_full);
       }
       if (rec) {
@@ -485,72 +602,208 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
         atomicAdd((unsigned long long*)g.dbg + 13, (unsigned long long)n_stages);
       }
     }
-  } else if (warp <= 12 && !skip_tile) {
-    // ------------------------------------------------------------------------ drain warps 9..12, then the epilogue
-    const int quarter = warp & 3;
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    for (int blk = 0; blk < n_blocks; ++blk) {
-      mbar_wait(blk_full, (uint32_t)blk & 1u);
-      tc_fence_after();
-      if (n_blocks > 1) {  // master (+)= work, round-to-nearest
-        for (int c0 = 0; c0 < n_tile; c0 += 32) {
-          uint32_t w[32], m[32];
-          tm_ld32(t_work + lane_addr + (uint32_t)c0, w);
-          if (blk > 0) tm_ld32(t_master + lane_addr + (uint32_t)c0, m);
-          tm_ld_wait();
-          if (blk > 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) + __uint_as_float(m[i]));
-          }
-          tm_st32(t_master + lane_addr + (uint32_t)c0, w);
-        }
-        tm_st_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(blk_done);
-    }
-    const uint32_t t_acc = (n_blocks > 1 ? t_master : t_work) + lane_addr;
-    tc_fence_after();
-    if (MODE == 0) {
-      const long long col = (long long)m0 + quarter * 32 + lane;  // this thread's sample
-      const int acc_row = g.pre_row >= 0 ? g.pre_row : g.out_row;
-      const int n_write = min(TN, g.n_out - n0);                   // padded outputs of this tile
-      vm::with_act(g.act, [&](auto tag) {
-        constexpr int ACT = decltype(tag)::value;
-        for (int c0 = 0; c0 < n_write; c0 += 32) {
-          uint32_t w[32];
-          if (n_stages > 0) { tm_ld32(t_acc + (uint32_t)c0, w); tm_ld_wait(); }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int j = n0 + c0 + i;
-            if (c0 + i < n_write) {
-              float x = (n_stages > 0 ? __uint_as_float(w[i]) : 0.0f) + (g.b_off >= 0 ? __ldg(g.par + g.b_off + j) : 0.0f);
-              if (g.accumulate) x += g.rows[(long long)(acc_row + j) * g.C + col];
-              if (g.pre_row >= 0) g.rows[(long long)(g.pre_row + j) * g.C + col] = x;
-              g.rows[(long long)(g.out_row + j) * g.C + col] = vm::act_fwd(ACT, x);
-            }
-          }
-        }
-      });
-    } else if (n_stages > 0) {
-      const int i = m0 + quarter * 32 + lane;  // TMEM lane = input feature
-      for (int c0 = 0; c0 < n_valid; c0 += 32) {
-        uint32_t w[32];
-        tm_ld32(t_acc + (uint32_t)c0, w);
-        tm_ld_wait();
-        if (i < g.n_in) {
-          float* dst = g.grad + g.w_off + (long long)i * g.ld + n0 + c0;
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (c0 + q < n_valid) atomicAdd(dst + q, __uint_as_float(w[q]));
-        }
-      }
-    }
+  } else if (warp <= NSW + 4 && !skip_tile) {
+    drain_epilogue<MODE, false>(g, warp, lane, n_blocks, n_stages, n_tile, n_valid, n0, m0, t_work, t_master, blk_full, blk_done);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster -- two neighbouring sample tiles (LINEAR) / input-feature tiles
+// (LINEAR_DW) -- run ONE 256 x 256 x 8 MMA per step.  Each CTA loads and splits its own 128 A rows and only HALF of the B
+// tile (the tensor core of each SM reads the other half from its peer), so per SM and stage the loads drop from 24 to
+// 16 KB, the split from 48 to 32 KB of shared-memory traffic and the MMA operand reads from 72 to 48 KB: the one-CTA
+// kernel above is bound by exactly that shared-memory bandwidth (6 MMAs of a stage alone need ~1060 cycles of it, the
+// split and the fills the rest of the measured 1750).  The leader (cluster rank 0) issues the MMAs and owns the barriers
+// the splitters / drain warps of both CTAs arrive on (full, blk_done); MMA completion is multicast to both CTAs' copies
+// of raw_empty / lo_empty / blk_full.  Tensor loads only (there is no cp.async pair kernel).
+constexpr int PRS = 7, PLS = 5;                      // raw / lo ring depths of the pair kernel (16 KB stages)
+constexpr int PB_BYTES = (TN / 2) * KS * 4, PSTAGE = A_BYTES + PB_BYTES;
+static_assert(1024 + (size_t)(PRS + PLS) * PSTAGE + 256 <= SMEM_BYTES, "pair rings exceed the allocation");
+
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS + 32, 1)
+vg_gemm3_pair(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* raw = base;                                  // [PRS][A | B half]
+  unsigned char* lo = base + (size_t)PRS * PSTAGE;            // [PLS][A | B half]
+  uint64_t* bars = (uint64_t*)(lo + (size_t)PLS * PSTAGE);
+  uint64_t* full = bars;                 // [PLS]  leader's copy: 8 arrivals (four warps of the owning set in each CTA)
+  uint64_t* lo_empty = full + PLS;        // [PLS]  MMA commit, multicast
+  uint64_t* raw_empty = lo_empty + PLS;   // [PRS] MMA commit, multicast
+  uint64_t* blk_full = raw_empty + PRS;  // [1]   MMA commit, multicast
+  uint64_t* blk_done = blk_full + 1;     // [1]   leader's copy: 8 arrivals
+  uint64_t* raw_full = blk_done + 1;     // [PRS] this CTA's tensor loads have landed
+  uint32_t* tmem_slot = (uint32_t*)(raw_full + PRS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+
+  const int n0 = blockIdx.y * TN;
+  const int n_valid = min(TN, g.b_rows - n0);
+  const int n_tile = (max(n_valid, 16) + 15) & ~15;      // MMA N; this CTA holds rows [rank * n_tile / 2, + n_tile / 2) of the B tile
+  const int n_half = n_tile >> 1, b_row0 = n0 + (int)rank * n_half;
+  const int m0 = blockIdx.x * TM;                        // first sample (LINEAR) / input feature (DW) of THIS CTA's half of M = 256
+  int k_begin = 0, k_end = g.K;
+  if (MODE == 0) {
+    if (g.kr.enabled) {
+      int l = 1 << 30, h = 0;
+      for (int half = 0; half < 2; ++half) {
+        const int tl = 2 * (int)blockIdx.y + half;
+        if (tl < 8 && half * 128 < n_valid && g.kr.hi[tl] > g.kr.lo[tl]) { l = min(l, (int)g.kr.lo[tl]); h = max(h, (int)g.kr.hi[tl]); }
+      }
+      k_begin = h > 0 ? l * 16 : 0;
+      k_end = h > 0 ? min(g.K, h * 16) : 0;
+    }
+  } else {
+    k_begin = blockIdx.z * g.k_slab; k_end = min(g.K, k_begin + g.k_slab);
+  }
+  const int n_stages = k_end > k_begin ? (k_end - k_begin + KS - 1) / KS : 0;
+  const int n_blocks = (n_stages + BLK - 1) / BLK;
+
+  if (tid == 0) {
+    for (int s = 0; s < PLS; ++s) { mbar_init(full + s, 8); mbar_init(lo_empty + s, 1); }
+    for (int s = 0; s < PRS; ++s) { mbar_init(raw_empty + s, 1); mbar_init(raw_full + s, 1); }
+    mbar_init(blk_full, 1);
+    mbar_init(blk_done, 8);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  tc_fence_before();
+  cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_work = tmem, t_master = tmem + TN;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ splitters: 1024 pieces per stage, 8 per thread of the owning set
+    const int set = warp >> 2, ts = tid & 127;
+    constexpr int PA = A_BYTES / 16 / 128, PB = PB_BYTES / 16 / 128;  // 4, 4
+    float bsum[PB];
+#pragma unroll
+    for (int e = 0; e < PB; ++e) bsum[e] = 0.0f;
+    auto low = [](const float4& x) {
+      float4 l;
+      l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+      l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+      l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+      l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+      return l;
+    };
+    for (int t = set; t < n_stages; t += 2) {
+      if (lane == 0) {
+        mbar_wait(raw_full + t % PRS, (uint32_t)(t / PRS) & 1u);
+        if (t >= PLS) mbar_wait(lo_empty + t % PLS, (uint32_t)(t / PLS - 1) & 1u);
+      }
+      __syncwarp();
+      const unsigned char* sr = raw + (size_t)(t % PRS) * PSTAGE;
+      unsigned char* sl = lo + (size_t)(t % PLS) * PSTAGE;
+      float4 x[PA + PB];
+#pragma unroll
+      for (int e = 0; e < PA + PB; ++e)
+        if (e < PA || (ts >> 2) + 32 * (e - PA) < n_half) x[e] = *reinterpret_cast<const float4*>(sr + 16 * (ts + 128 * e));
+#pragma unroll
+      for (int e = 0; e < PA + PB; ++e)
+        if (e < PA || (ts >> 2) + 32 * (e - PA) < n_half) {
+          *reinterpret_cast<float4*>(sl + 16 * (ts + 128 * e)) = low(x[e]);
+          if (MODE == 1 && e >= PA) bsum[e - PA] += (x[e].x + x[e].y) + (x[e].z + x[e].w);
+        }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(full + t % PLS);
+    }
+    if (MODE == 1 && blockIdx.x < 2 && g.gb_off >= 0) {  // bias gradient from the first pair of every column of tiles: each CTA its half of the g rows
+#pragma unroll
+      for (int e = 0; e < PB; ++e) {
+        float a = bsum[e];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        const int r = (ts >> 2) + 32 * e;
+        if ((ts & 3) == 0 && r < n_half && b_row0 + r < g.b_rows) atomicAdd(g.grad + g.gb_off + b_row0 + r, a);
+      }
+    }
+  } else if (warp == 13) {
+    if (lane == 0) {  // -------------------------------------------------------------------- tensor-load producer (each CTA its own operands)
+      for (int t = 0; t < n_stages; ++t) {
+        if (t >= PRS) mbar_wait(raw_empty + t % PRS, (uint32_t)(t / PRS - 1) & 1u);
+        const int k0 = k_begin + t * KS;
+        const uint32_t sa = smem_u32(raw + (size_t)(t % PRS) * PSTAGE), sb = sa + A_BYTES;
+        vmtc::mbar_expect_tx(raw_full + t % PRS, PSTAGE);
+        if (MODE == 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_2d(sa + 2048u * c, &map_a, m0 + 32 * c, k0, raw_full + t % PRS);
+        } else {
+          tma_2d(sa, &map_a, k0, m0, raw_full + t % PRS);
+        }
+        tma_2d(sb, &map_b, k0, b_row0, raw_full + t % PRS);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0 && rank == 0) {  // ------------------------------------------------------- MMA issuer: the leader, for both SMs
+      const bool rec = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long w_full = 0, w_blk = 0;
+      const long long t_start = rec ? clock64() : 0;
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MODE == 0 ? (1u << 15) : 0u) | ((uint32_t)(n_tile >> 3) << 17) |
+                             ((uint32_t)((2 * TM) >> 4) << 24);
+      for (int t = 0; t < n_stages; ++t) {
+        const int blk = t / BLK;
+        long long c0 = rec ? clock64() : 0;
+        if (t % BLK == 0 && blk > 0) mbar_wait_cluster(blk_done, (uint32_t)(blk - 1) & 1u);
+        long long c1 = rec ? clock64() : 0;
+        mbar_wait_cluster(full + t % PLS, (uint32_t)(t / PLS) & 1u);
+        if (rec) { w_blk += c1 - c0; w_full += clock64() - c1; }
+        tc_fence_after();
+        const uint32_t sr = smem_u32(raw + (size_t)(t % PRS) * PSTAGE), sl = smem_u32(lo + (size_t)(t % PLS) * PSTAGE);
+        uint64_t da_hi, da_lo, adv_a;
+        if (MODE == 0) { da_hi = desc_sw(sr, 2048, 512, 1); da_lo = desc_sw(sl, 2048, 512, 1); adv_a = 1024 >> 4; }
+        else { da_hi = desc_sw(sr, 16, 512, 4); da_lo = desc_sw(sl, 16, 512, 4); adv_a = 32 >> 4; }
+        const uint64_t db_hi = desc_sw(sr + A_BYTES, 16, 512, 4), db_lo = desc_sw(sl + A_BYTES, 16, 512, 4);
+#pragma unroll
+        for (int ks = 0; ks < KS / 8; ++ks) {
+          const uint64_t aa = adv_a * ks, ab = (uint64_t)(2 * ks);
+          mma_tf32_pair(t_work, da_lo + aa, db_hi + ab, idesc, (t % BLK == 0 && ks == 0) ? 0u : 1u);
+          mma_tf32_pair(t_work, da_hi + aa, db_lo + ab, idesc, 1u);
+          mma_tf32_pair(t_work, da_hi + aa, db_hi + ab, idesc, 1u);
+        }
+        umma_commit_pair(raw_empty + t % PRS);
+        umma_commit_pair(lo_empty + t % PLS);
+        if (t % BLK == BLK - 1 || t == n_stages - 1) umma_commit_pair(blk_full);
+      }
+      if (rec) {
+        atomicAdd((unsigned long long*)g.dbg + 10, (unsigned long long)w_full);
+        atomicAdd((unsigned long long*)g.dbg + 11, (unsigned long long)w_blk);
+        atomicAdd((unsigned long long*)g.dbg + 12, (unsigned long long)(clock64() - t_start));
+        atomicAdd((unsigned long long*)g.dbg + 13, (unsigned long long)n_stages);
+      }
+    }
+  } else if (warp <= 12) {
+    drain_epilogue<MODE, true>(g, warp, lane, n_blocks, n_stages, n_tile, n_valid, n0, m0, t_work, t_master, blk_full, blk_done);
+  }
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves (or frees tensor memory) while the peer may still read this CTA's shared memory / arrive here
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
 // ---- host: tensor maps of the TMA-fed variant (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda)
@@ -575,14 +828,17 @@ inline bool make_tmap(CUtensorMap* m, const float* base, long long inner, long l
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// (The CTA-pair kernel is kept for the record and behind SURJ_B200_GEMM3_TMA bits 2 / 3: see vm_global.cu.)
 // maps of a launch: MODE 0 (LINEAR): A = in rows [K][samples] read in boxes {32 samples, 16 k}; MODE 1 (LINEAR_DW): A = in rows
 // [n_in][samples] in boxes {16 samples, 128 rows}.  B: rows [b_rows][K] in boxes {16 k, 256 rows}.  Out-of-bounds rows / k read as zeros.
-inline bool make_maps(int mode, const Args& a, long long samples, CUtensorMap* ma, CUtensorMap* mb) {
+// pair: the CTA-pair kernel, whose CTAs load half a B tile each (boxes of 128 rows).
+inline bool make_maps(int mode, const Args& a, long long samples, bool pair, CUtensorMap* ma, CUtensorMap* mb) {
+  const int bn = pair ? TN / 2 : TN;
   if (mode == 0)
     return make_tmap(ma, a.a_base, samples, a.a_rows, a.a_pitch, 32, KS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
-           make_tmap(mb, a.b_base, a.K, a.b_rows, a.b_pitch, KS, TN, CU_TENSOR_MAP_SWIZZLE_64B);
+           make_tmap(mb, a.b_base, a.K, a.b_rows, a.b_pitch, KS, bn, CU_TENSOR_MAP_SWIZZLE_64B);
   return make_tmap(ma, a.a_base, a.K, a.a_rows, a.a_pitch, KS, TM, CU_TENSOR_MAP_SWIZZLE_64B) &&
-         make_tmap(mb, a.b_base, a.K, a.b_rows, a.b_pitch, KS, TN, CU_TENSOR_MAP_SWIZZLE_64B);
+         make_tmap(mb, a.b_base, a.K, a.b_rows, a.b_pitch, KS, bn, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 }  // namespace vmg

@@ -648,7 +648,10 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   }();
   const bool use_tc_lin = tc_mode == 1 || tc_mode == 2 || tc_mode == 5 || tc_mode == 6, use_tc_dw = tc_mode == 1 || tc_mode == 3 || tc_mode == 5;
   const bool gemm3 = tc_mode == 6;
-  // operands of the gemm3 kernels by TMA tensor loads (bit 0: LINEAR_DW, bit 1: LINEAR); 0: cp.async loaders
+  // operands of the gemm3 kernels by TMA tensor loads (bit 0: LINEAR_DW, bit 1: LINEAR); 0: cp.async loaders;
+  // bits 2 / 3: CTA pairs (cta_group::2, M = 256) for LINEAR_DW / LINEAR where the grid's x extent is even -- correct, but
+  // measured slower than one CTA per tile (cfg4 train step, weight-gradient / input-gradient products: 122 / 136 ms
+  // against 112 / 129 ms), so off by default
   static const int gemm3_tma = [] { const char* e = getenv("SURJ_B200_GEMM3_TMA"); return e ? atoi(e) : 3; }();
   static const bool use_tc = [] {
     const bool on = true;
@@ -660,6 +663,8 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
       cudaFuncSetAttribute(vmg::vg_gemm3<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
       cudaFuncSetAttribute(vmg::vg_gemm3<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
       cudaFuncSetAttribute(vmg::vg_gemm3<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
+      cudaFuncSetAttribute(vmg::vg_gemm3_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
+      cudaFuncSetAttribute(vmg::vg_gemm3_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
     }
     return on;
   }();
@@ -807,7 +812,9 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           dim3 grid(cols / vmg::TM, (op.a[5] + vmg::TN - 1) / vmg::TN);
           prof::Scope ps(st, prof::LINEAR_TC, fl);
           CUtensorMap ma{}, mb{};
-          if ((gemm3_tma & 2) && vmg::make_maps(0, a, cols, &ma, &mb)) vmg::vg_gemm3<0, true><<<grid, vmg::THREADS + 32, vmg::SMEM_BYTES, st>>>(a, ma, mb);
+          if ((gemm3_tma & 8) && grid.x % 2 == 0 && vmg::make_maps(0, a, cols, true, &ma, &mb))
+            vmg::vg_gemm3_pair<0><<<grid, vmg::THREADS + 32, vmg::SMEM_BYTES, st>>>(a, ma, mb);
+          else if ((gemm3_tma & 2) && vmg::make_maps(0, a, cols, false, &ma, &mb)) vmg::vg_gemm3<0, true><<<grid, vmg::TMA_THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
           else vmg::vg_gemm3<0, false><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
         } else if (pipe && tci.w_off[pc] >= 0) {  // tcgen05 3xTF32, TMA-fed pipeline on pre-tiled operands
           const int nkb = (op.a[1] + vmtc::PBK - 1) / vmtc::PBK;
@@ -852,7 +859,9 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           dim3 grid(ti, tj, (cols + a.k_slab - 1) / a.k_slab);
           prof::Scope ps(st, prof::DW_TC, fl);
           CUtensorMap ma{}, mb{};
-          if ((gemm3_tma & 1) && vmg::make_maps(1, a, cols, &ma, &mb)) vmg::vg_gemm3<1, true><<<grid, vmg::THREADS + 32, vmg::SMEM_BYTES, st>>>(a, ma, mb);
+          if ((gemm3_tma & 4) && grid.x % 2 == 0 && a.skip == 0ull && vmg::make_maps(1, a, cols, true, &ma, &mb))
+            vmg::vg_gemm3_pair<1><<<grid, vmg::THREADS + 32, vmg::SMEM_BYTES, st>>>(a, ma, mb);
+          else if ((gemm3_tma & 1) && vmg::make_maps(1, a, cols, false, &ma, &mb)) vmg::vg_gemm3<1, true><<<grid, vmg::TMA_THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
           else vmg::vg_gemm3<1, false><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
         } else if (use_tc && use_tc_dw && NA >= 32 && NG >= 32) {
           // sample slabs sized so the grid fills the machine about twice (2 CTAs per SM x 148 SMs x 2)
