@@ -800,7 +800,8 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
         const double fl = 2.0 * tci.nnz[pc] * (double)cols;
         // (long contractions only -- the input gradient through a spline layer's 1544 .. 6176 thetas; on K <= 512 its
         // one-tile-per-CTA set-up costs more than it saves: cfg5's MADE layers measured 777 vs 520 ms per train step)
-        if (gemm3 && pc > grad_from && tc_linear_op(op) && op.a[1] >= 1024) {  // cp.async-fed 3xTF32 tcgen05 kernel straight from the rows and the staged weights
+        static const int gemm3_min_k = [] { const char* e = getenv("SURJ_B200_GEMM3_MINK"); return e ? atoi(e) : 1024; }();
+        if (gemm3 && pc > grad_from && tc_linear_op(op) && op.a[1] >= gemm3_min_k) {  // cp.async-fed 3xTF32 tcgen05 kernel straight from the rows and the staged weights
           vmg::Args a{};
           a.a_base = k.rows + (size_t)op.a[0] * C; a.a_pitch = C; a.a_rows = op.a[1];
           a.b_base = k.par + op.a[10]; a.b_pitch = op.a[11]; a.b_rows = op.a[12];
@@ -883,6 +884,12 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
       } else {
         size_t e = pc;
         while (e < ops.size() && ops[e].code != vm::OP_LINEAR && ops[e].code != vm::OP_LINEAR_DW && (e == pc || tci.maf_at[e] < 0)) ++e;
+        static const bool op_dbg = getenv("SURJ_B200_OP_DBG") != nullptr;
+        if (op_dbg && base == 0) {  // the per-sample runs of the program, with the rows each op touches
+          fprintf(stderr, "[op dbg] per-sample run at %zu:", pc);
+          for (size_t q = pc; q < e; ++q) fprintf(stderr, " (%d: %d %d %d %d)", ops[q].code, ops[q].a[0], ops[q].a[1], ops[q].a[2], ops[q].a[3]);
+          fprintf(stderr, "\n");
+        }
         prof::Scope ps(st, prof::ELEM, 0.0);
         vm::vg_elem<<<cols / 128, 128, 0, st>>>(d_ops + pc, (int)(e - pc), first ? 1 : 0, io, k.rows, C, base, B, P.itab,
                                               k.scal, k.scal_g, k.loss);
