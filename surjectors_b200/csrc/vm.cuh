@@ -148,6 +148,21 @@ VM_DEV float act_bwd(int act, float a, float g) {
   }
 }
 
+// act_bwd with the sigmoid of swish / sigmoid / softplus units from ex2.approx + rcp.approx (relative error ~2^-21 on a factor
+// of a cotangent; the gradient bound is 1e-4 of the tensor scale).  The per-op executor's ACT_BWD sweep is otherwise
+// issue-bound, not HBM-bound: accurate expf + IEEE division are ~30 of its ~40 instructions per element.
+VM_DEV float act_bwd_fast(int act, float a, float g) {
+  if (act == ACT_SWISH || act == ACT_SIGMOID || act == ACT_SOFTPLUS) {
+    float e, s;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
+    if (act == ACT_SWISH) return g * (s * (1.0f + a * (1.0f - s)));
+    if (act == ACT_SIGMOID) return g * s * (1.0f - s);
+    return g * s;
+  }
+  return act_bwd(act, a, g);
+}
+
 // Runs f(std::integral_constant<int, ACT>{}) for the runtime activation code `act`.  Epilogues that apply an activation to
 // an unrolled register tile call this ONCE around the loop: each activation gets its own compact copy of the loop,
 // instead of the whole switch (tanhf, expm1f, ... inlined) being repeated per element -- that repetition made

@@ -55,7 +55,7 @@ constexpr int LOADERS = 256, THREADS = 416;
 //   raw 6, lo 2, 2 sets of 4 warps: 1750 / 145 / 154     raw 4, lo 4, 4 sets of 2 warps: 1840 / 154 / 158
 //   raw 5, lo 3, 2 sets of 4 warps: 1310 / 112 / 130     raw 5, lo 3, 3 sets of 4 warps (576 threads, drain spills): 1660 / 138 / 160
 constexpr int TRS = 5, TLS = 3, TSETS = 2, TSW = 8;   // raw / lo ring depths, splitter sets, splitter warps
-constexpr int TMA_THREADS = (TSW + 6) * 32;            // + MMA issuer, four drain warps, tensor-load producer
+constexpr int TMA_THREADS = (TSW + 7) * 32;            // + MMA issuer, four drain warps, two tensor-load producers (raw ring, lo ring)
 constexpr size_t SMEM_BYTES = 1024 + (size_t)(RS + LS) * STAGE_BYTES + 256;
 static_assert(SMEM_BYTES <= 227 * 1024, "rings exceed the shared memory of an SM");
 
@@ -134,6 +134,7 @@ struct Args {
   float* rows; long long C;                            // row workspace
   int out_row, pre_row, n_out, b_off, act, accumulate; // n_out: padded outputs written
   const float* par;
+  int ab_on, ab_pre_row, ab_n, ab_act;                 // the OP_ACT_BWD that follows, fused: out[j] = act'(rows[ab_pre_row + j]) * out[j], j < ab_n
   // DW epilogue
   float* grad; int w_off, ld, gb_off, n_in;            // grad[w_off + i * ld + j], grad[gb_off + j]
   VmKRange kr;                                         // LINEAR: k-stage range per 128-output tile (structural zeros), by value
@@ -199,23 +200,51 @@ __device__ __forceinline__ void drain_epilogue(const Args& g, int warp, int lane
     const long long col = (long long)m0 + quarter * 32 + lane;  // this thread's sample
     const int acc_row = g.pre_row >= 0 ? g.pre_row : g.out_row;
     const int n_write = min(TN, g.n_out - n0);                   // padded outputs of this tile
-    vm::with_act(g.act, [&](auto tag) {
-      constexpr int ACT = decltype(tag)::value;
-      for (int c0 = 0; c0 < n_write; c0 += 32) {
-        uint32_t w[32];
-        if (n_stages > 0) { tm_ld32(t_acc + (uint32_t)c0, w); tm_ld_wait(); }
+    if (g.ab_on) {
+      // input-gradient product followed by the activation derivative (no bias, identity, no accumulate: vm_global.cu):
+      // the 32 pre-activations of a column batch are requested together, before any of this batch's stores
+      vm::with_act(g.ab_act, [&](auto tag) {
+        constexpr int ACT = decltype(tag)::value;
+        for (int c0 = 0; c0 < n_write; c0 += 32) {
+          uint32_t w[32];
+          float pre[32];
+          if (n_stages > 0) tm_ld32(t_acc + (uint32_t)c0, w);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = n0 + c0 + i;
-          if (c0 + i < n_write) {
-            float x = (n_stages > 0 ? __uint_as_float(w[i]) : 0.0f) + (g.b_off >= 0 ? __ldg(g.par + g.b_off + j) : 0.0f);
-            if (g.accumulate) x += g.rows[(long long)(acc_row + j) * g.C + col];
-            if (g.pre_row >= 0) g.rows[(long long)(g.pre_row + j) * g.C + col] = x;
-            g.rows[(long long)(g.out_row + j) * g.C + col] = vm::act_fwd(ACT, x);
+          for (int i = 0; i < 32; ++i) {
+            const int j = n0 + c0 + i;
+            pre[i] = (c0 + i < n_write && j < g.ab_n) ? g.rows[(long long)(g.ab_pre_row + j) * g.C + col] : 0.0f;
+          }
+          if (n_stages > 0) tm_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = n0 + c0 + i;
+            if (c0 + i < n_write) {
+              float x = n_stages > 0 ? __uint_as_float(w[i]) : 0.0f;
+              if (j < g.ab_n) x = vm::act_bwd_fast(ACT, pre[i], x);
+              g.rows[(long long)(g.out_row + j) * g.C + col] = x;
+            }
           }
         }
-      }
-    });
+      });
+    } else {
+      vm::with_act(g.act, [&](auto tag) {
+        constexpr int ACT = decltype(tag)::value;
+        for (int c0 = 0; c0 < n_write; c0 += 32) {
+          uint32_t w[32];
+          if (n_stages > 0) { tm_ld32(t_acc + (uint32_t)c0, w); tm_ld_wait(); }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = n0 + c0 + i;
+            if (c0 + i < n_write) {
+              float x = (n_stages > 0 ? __uint_as_float(w[i]) : 0.0f) + (g.b_off >= 0 ? __ldg(g.par + g.b_off + j) : 0.0f);
+              if (g.accumulate) x += g.rows[(long long)(acc_row + j) * g.C + col];
+              if (g.pre_row >= 0) g.rows[(long long)(g.pre_row + j) * g.C + col] = x;
+              g.rows[(long long)(g.out_row + j) * g.C + col] = vm::act_fwd(ACT, x);
+            }
+          }
+        }
+      });
+    }
   } else if (n_stages > 0) {
     const int i = m0 + quarter * 32 + lane;  // TMEM lane = input feature
     for (int c0 = 0; c0 < n_valid; c0 += 32) {
@@ -234,9 +263,12 @@ __device__ __forceinline__ void drain_epilogue(const Args& g, int warp, int lane
 
 // MODE 0: LINEAR, grid (sample tiles, ceil(n_out / 256)).   MODE 1: LINEAR_DW, grid (ceil(n_in / 128), ceil(n_out / 256), slabs).
 // TMA: tensor-load producer warp (THREADS + 32 threads, map_a / map_b from make_maps below); else cp.async loaders, maps unused.
-template <int MODE, bool TMA>
+// BLO (TMA, LINEAR): the B operand is a weight matrix whose lo part was computed once per call (vg_par_lo): a second
+// producer thread tensor-loads it from map_blo straight into the lo ring, and the splitters only touch the activation tile.
+template <int MODE, bool TMA, bool BLO = false>
 __global__ void __launch_bounds__(TMA ? TMA_THREADS : THREADS, 1)
-vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
+vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+         const __grid_constant__ CUtensorMap map_blo) {
   constexpr int RSx = TMA ? TRS : RS, LSx = TMA ? TLS : LS;   // ring depths of this variant
   constexpr int NSW = TMA ? TSW : 8;                          // warps 0 .. NSW-1 load / split, NSW issues the MMAs, NSW+1 .. NSW+4 drain, NSW+5 produces
   extern __shared__ unsigned char smem_raw[];
@@ -285,7 +317,7 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
   }
 
   if (tid == 0) {
-    for (int s = 0; s < LSx; ++s) { mbar_init(full + s, TMA ? TSW / TSETS : LOADERS / 64); mbar_init(lo_empty + s, 1); }
+    for (int s = 0; s < LSx; ++s) { mbar_init(full + s, TMA ? TSW / TSETS + (BLO ? 1 : 0) : LOADERS / 64); mbar_init(lo_empty + s, 1); }
     for (int s = 0; s < RSx; ++s) { mbar_init(raw_empty + s, 1); mbar_init(raw_full + s, 1); }
     mbar_init(blk_full, 1);
     mbar_init(blk_done, 4);
@@ -340,12 +372,12 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
 #pragma unroll
           for (int q = 0; q < HALF; ++q) {
             const int e = h * HALF + q;
-            if (e < PA || (ts >> 2) + (SETT / 4) * (e - PA) < n_tile) x[q] = *reinterpret_cast<const float4*>(sr + 16 * (ts + SETT * e));
+            if (e < PA || (!BLO && (ts >> 2) + (SETT / 4) * (e - PA) < n_tile)) x[q] = *reinterpret_cast<const float4*>(sr + 16 * (ts + SETT * e));
           }
 #pragma unroll
           for (int q = 0; q < HALF; ++q) {
             const int e = h * HALF + q;
-            if (e < PA || (ts >> 2) + (SETT / 4) * (e - PA) < n_tile) {
+            if (e < PA || (!BLO && (ts >> 2) + (SETT / 4) * (e - PA) < n_tile)) {
               *reinterpret_cast<float4*>(sl + 16 * (ts + SETT * e)) = low(x[q]);
               if (MODE == 1 && e >= PA) bsum[e - PA] += (x[q].x + x[q].y) + (x[q].z + x[q].w);
             }
@@ -393,6 +425,14 @@ vg_gemm3(const __grid_constant__ Args g, const __grid_constant__ CUtensorMap map
           tma_2d(sa, &map_a, k0, m0, raw_full + t % RSx);
         }
         tma_2d(sb, &map_b, k0, n0, raw_full + t % RSx);
+      }
+    }
+  } else if (TMA && BLO && warp == NSW + 6) {
+    if (lane == 0 && !skip_tile) {  // ------------------------------------------------------ lo-ring producer: the weights' lo part
+      for (int t = 0; t < n_stages; ++t) {
+        if (t >= LSx) mbar_wait(lo_empty + t % LSx, (uint32_t)(t / LSx - 1) & 1u);
+        vmtc::mbar_expect_tx(full + t % LSx, B_BYTES);   // arrive + expect: the stage is full when this and the splitters' arrivals are in
+        tma_2d(smem_u32(lo + (size_t)(t % LSx) * STAGE_BYTES) + A_BYTES, &map_blo, k_begin + t * KS, n0, full + t % LSx);
       }
     }
   } else if (warp < 8) {
@@ -827,6 +867,17 @@ inline bool make_tmap(CUtensorMap* m, const float* base, long long inner, long l
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer}, es[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// the lo image of a LINEAR weight operand: same geometry as map_b on the lo copy of the staged parameters
+inline bool make_blo_map(const Args& a, const float* par, const float* par_lo, CUtensorMap* m) {
+  return make_tmap(m, par_lo + (a.b_base - par), a.K, a.b_rows, a.b_pitch, KS, TN, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+// lo[i] = w[i] - trunc_tf32(w[i]) over the staged parameters, once per backward call
+__global__ void vg_par_lo(const float* __restrict__ par, float* __restrict__ lo, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float w = par[i];
+    lo[i] = w - __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+  }
 }
 // (The CTA-pair kernel is kept for the record and behind SURJ_B200_GEMM3_TMA bits 2 / 3: see vm_global.cu.)
 // maps of a launch: MODE 0 (LINEAR): A = in rows [K][samples] read in boxes {32 samples, 16 k}; MODE 1 (LINEAR_DW): A = in rows

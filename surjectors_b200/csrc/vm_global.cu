@@ -561,7 +561,7 @@ const VmTcInfo& tc_info(const VmPlan* v, int prog) {
 }
 
 struct Carve {
-  float *par, *grad, *scal, *scal_g, *loss, *rows, *w_tiles, *a_tiles;
+  float *par, *par_lo, *grad, *scal, *scal_g, *loss, *rows, *w_tiles, *a_tiles;  // par_lo: TF32 lo part of the staged parameters (gemm3 LINEAR)
   unsigned char* img;   // fp16 hi / lo weight images of the fused groups
   unsigned* scales;     // max |w| per image matrix (float bits)
   size_t total;
@@ -573,6 +573,7 @@ Carve carve(const VmPlan* v, void* ws, int C, int prog) {
   auto take = [&](size_t floats) { float* p = ws ? (float*)((char*)ws + o) : nullptr; o += a256(floats * 4); return p; };
   k.par = take(v->stage.size());
   k.grad = take(backward ? v->stage.size() : 1);
+  k.par_lo = take(backward ? v->stage.size() : 1);
   k.scal = take(std::max(v->n_scalars, 1));
   k.scal_g = take(std::max(v->n_scalars, 1));
   k.loss = take(1);
@@ -663,6 +664,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
       cudaFuncSetAttribute(vmg::vg_gemm3<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
       cudaFuncSetAttribute(vmg::vg_gemm3<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
       cudaFuncSetAttribute(vmg::vg_gemm3<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
+      cudaFuncSetAttribute(vmg::vg_gemm3<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
       cudaFuncSetAttribute(vmg::vg_gemm3_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
       cudaFuncSetAttribute(vmg::vg_gemm3_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vmg::SMEM_BYTES);
     }
@@ -690,6 +692,11 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   }
   // tensor-core LINEAR ops: split (hi / lo TF32) and tile every weight matrix they use, once per call
   const VmTcInfo& tci = tc_info(v, prog);
+  static const int gemm3_blo = [] { const char* e = getenv("SURJ_B200_GEMM3_BLO"); return e ? atoi(e) : 1; }();
+  if (backward && gemm3_blo) {  // lo part of every staged parameter: the weight operand of vg_gemm3's LINEAR is tensor-loaded pre-split
+    prof::Scope ps(st, prof::TILE, 0.0);
+    vmg::vg_par_lo<<<148 * 8, 256, 0, st>>>(k.par, k.par_lo, n_par);
+  }
   // Default: the TMA-fed pipelined kernel on pre-tiled operands.  It is L2-bandwidth bound (hi + lo planes of both
   // operands stream per 128x128 tile: 16 FLOP/B, profiles/r1_linear_pipe_ncu.md) but issues ~10x fewer instructions than
   // the register-staged kernel (SURJ_B200_TC=1), whose in-CTA split / staging is ALU-bound: measured at batch 262144,
@@ -810,13 +817,27 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           a.accumulate = op.a[8]; a.par = k.par;
           a.kr = tci.kr[pc];
           a.dbg = fused_dbg_buffer();
+          // the activation derivative that follows an input-gradient product (emit_mlp_bwd: LINEAR into the previous layer's
+          // post rows, then OP_ACT_BWD on them) goes into the product's epilogue: one read and one write of the rows less
+          // (measured neutral on cfg4 -- per-sample ops -14 ms, the product's exposed epilogue +12 ms per train step -- so off by default)
+          static const bool fuse_ab = [] { const char* e = getenv("SURJ_B200_FUSE_ACT_BWD"); return e && atoi(e) != 0; }();
+          bool fused_ab = false;
+          if (fuse_ab && pc + 1 < ops.size() && ops[pc + 1].code == vm::OP_ACT_BWD && tci.maf_at[pc + 1] < 0 && ops[pc + 1].a[0] == op.a[4] &&
+              ops[pc + 1].a[2] <= op.a[5] && !op.a[8] && op.a[7] == vm::ACT_IDENTITY && op.a[9] < 0 && op.a[6] < 0) {
+            a.ab_on = 1; a.ab_pre_row = ops[pc + 1].a[1]; a.ab_n = ops[pc + 1].a[2]; a.ab_act = ops[pc + 1].a[3];
+            fused_ab = true;
+          }
           dim3 grid(cols / vmg::TM, (op.a[5] + vmg::TN - 1) / vmg::TN);
           prof::Scope ps(st, prof::LINEAR_TC, fl);
-          CUtensorMap ma{}, mb{};
+          CUtensorMap ma{}, mb{}, mlo{};
           if ((gemm3_tma & 8) && grid.x % 2 == 0 && vmg::make_maps(0, a, cols, true, &ma, &mb))
             vmg::vg_gemm3_pair<0><<<grid, vmg::THREADS + 32, vmg::SMEM_BYTES, st>>>(a, ma, mb);
-          else if ((gemm3_tma & 2) && vmg::make_maps(0, a, cols, false, &ma, &mb)) vmg::vg_gemm3<0, true><<<grid, vmg::TMA_THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
-          else vmg::vg_gemm3<0, false><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
+          else if ((gemm3_tma & 2) && vmg::make_maps(0, a, cols, false, &ma, &mb)) {
+            if (backward && gemm3_blo && vmg::make_blo_map(a, k.par, k.par_lo, &mlo))
+              vmg::vg_gemm3<0, true, true><<<grid, vmg::TMA_THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb, mlo);
+            else vmg::vg_gemm3<0, true><<<grid, vmg::TMA_THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb, mlo);
+          } else vmg::vg_gemm3<0, false><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb, mlo);
+          if (fused_ab) ++pc;  // (the ++pc below steps over the LINEAR)
         } else if (pipe && tci.w_off[pc] >= 0) {  // tcgen05 3xTF32, TMA-fed pipeline on pre-tiled operands
           const int nkb = (op.a[1] + vmtc::PBK - 1) / vmtc::PBK;
           { prof::Scope ps(st, prof::TILE, 0.0);
@@ -862,8 +883,8 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           CUtensorMap ma{}, mb{};
           if ((gemm3_tma & 4) && grid.x % 2 == 0 && a.skip == 0ull && vmg::make_maps(1, a, cols, true, &ma, &mb))
             vmg::vg_gemm3_pair<1><<<grid, vmg::THREADS + 32, vmg::SMEM_BYTES, st>>>(a, ma, mb);
-          else if ((gemm3_tma & 1) && vmg::make_maps(1, a, cols, false, &ma, &mb)) vmg::vg_gemm3<1, true><<<grid, vmg::TMA_THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
-          else vmg::vg_gemm3<1, false><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb);
+          else if ((gemm3_tma & 1) && vmg::make_maps(1, a, cols, false, &ma, &mb)) vmg::vg_gemm3<1, true><<<grid, vmg::TMA_THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb, ma);
+          else vmg::vg_gemm3<1, false><<<grid, vmg::THREADS, vmg::SMEM_BYTES, st>>>(a, ma, mb, ma);
         } else if (use_tc && use_tc_dw && NA >= 32 && NG >= 32) {
           // sample slabs sized so the grid fills the machine about twice (2 CTAs per SM x 148 SMs x 2)
           // (the bias gradient comes out of staging the g operand, so the tile rows cover the n_in real inputs only)

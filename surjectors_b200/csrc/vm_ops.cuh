@@ -369,7 +369,7 @@ VM_DEV bool exec_simple(Ctx<NT, S, FAR>& c, const Op& op, const Io& io, float& l
         for (int u = 0; u < UA; ++u) {
           if (k0 + u >= op.a[2]) break;
 #pragma unroll
-          for (int s = 0; s < S; ++s) c.row(op.a[0] + k0 + u)[s * NT] = act_bwd(op.a[3], a[u][s], g[u][s]);
+          for (int s = 0; s < S; ++s) c.row(op.a[0] + k0 + u)[s * NT] = FAR ? act_bwd_fast(op.a[3], a[u][s], g[u][s]) : act_bwd(op.a[3], a[u][s], g[u][s]);
         }
       }
       return true;
