@@ -8,16 +8,22 @@
 //   LINEAR_DW  grad[i][j] += sum_s in[i][s] g[j][s], grad[b][j] += sum_s g[j][s]  M = 128 inputs, N <= 256 outputs, K = samples
 //
 // Both read their operands as plain float32 straight from where they live -- rows [row][sample] of the workspace and
-// the staged parameters -- with cp.async into a shared-memory ring in the K-major no-swizzle UMMA layout (LINEAR's
-// activation operand is sample-major in memory: it is transposed on the fly by 4-byte cp.async, so no separate
-// re-tiling pass and no second copy of the activations exist).  The thread that loaded a 16-byte piece also splits it:
-// the tensor core reads the float32 bits as TF32 (it ignores the 13 low mantissa bits: hi = truncation, free) and the
-// thread writes lo = x - trunc(x) to a second ring; per 8-wide k step the issuing thread runs lo*hi + hi*lo + hi*hi
+// the staged parameters -- into a shared-memory ring: no separate re-tiling pass and no second copy of the activations
+// exist.  Two loader variants (template parameter TMA):
+//   * TMA (default): one thread issues tensor loads (cp.async.bulk.tensor.2d) that land in swizzled UMMA layouts -- K-major
+//     operands with the 64-byte swizzle, LINEAR's sample-major activations as an MN-major operand on the 32-byte-atom
+//     128-byte swizzle (details at tma_2d below); eight warps then only split;
+//   * cp.async (fallback when a tensor map cannot describe an operand: base not 16-byte aligned, pitch not a multiple of
+//     4 floats): eight loader warps copy 16-byte pieces (LINEAR's activations: 4-byte copies that transpose on the fly)
+//     into the K-major no-swizzle layout and split what they loaded.
+// The split: the tensor core reads the float32 bits as TF32 (it ignores the 13 low mantissa bits: hi = truncation, free)
+// and lo = x - trunc(x) goes to a second ring; per 8-wide k step the issuing thread runs lo*hi + hi*lo + hi*hi
 // (3xTF32, product error 2^-21).  The tensor core's accumulator add truncates, so only BLK = 256 k are accumulated
 // inside it; four drain warps add every finished block into a MASTER accumulator in tensor memory with round-to-nearest
 // adds (tcgen05.ld / FADD / tcgen05.st) -- N = 256 is the MMA shape that reaches the tensor pipe's rate (a 128-wide
 // MMA costs the same 140-cycle floor, tools/ubench/f16_probe.cu), and 2 x 256 columns are all of tensor memory.
-// Warp roles (416 threads): 0..7 load + split, 8 issues the MMAs, 9..12 drain / epilogue (TMEM lanes 32 * (warp % 4)).
+// Warp roles: 0..7 load / split, 8 issues the MMAs, 9..12 drain / epilogue (TMEM lanes 32 * (warp % 4)); TMA variant:
+// + 13 tensor-load producer (raw ring), 14 producer of the pre-split weight lo part (lo ring, BLO).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

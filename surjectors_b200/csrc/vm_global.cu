@@ -641,7 +641,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
   const int C = chunk_cols(B, v->n_rows);
   Carve k = carve(v, ws, C, prog);
   static const int tc_mode = [] {
-    // 6 (default): cp.async-fed, in-SM split 3xTF32 tcgen05 kernel for LINEAR and LINEAR_DW (vm_gemm3.cuh, no re-tiling pass);
+    // 6 (default): TMA-fed (cp.async fallback), in-SM split 3xTF32 tcgen05 kernel for LINEAR and LINEAR_DW (vm_gemm3.cuh, no re-tiling pass);
     // 5: TMA-fed pipelined tcgen05 LINEAR on re-tiled operands + register-staged tcgen05 LINEAR_DW; 1: register-staged tcgen05 for both;
     // 2 / 3: register-staged tcgen05 for LINEAR / LINEAR_DW only; 0: FP32 SIMT tiles only
     const char* e = getenv("SURJ_B200_TC");
@@ -808,7 +808,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
         // (long contractions only -- the input gradient through a spline layer's 1544 .. 6176 thetas; on K <= 512 its
         // one-tile-per-CTA set-up costs more than it saves: cfg5's MADE layers measured 777 vs 520 ms per train step)
         static const int gemm3_min_k = [] { const char* e = getenv("SURJ_B200_GEMM3_MINK"); return e ? atoi(e) : 1024; }();
-        if (gemm3 && pc > grad_from && tc_linear_op(op) && op.a[1] >= gemm3_min_k) {  // cp.async-fed 3xTF32 tcgen05 kernel straight from the rows and the staged weights
+        if (gemm3 && pc > grad_from && tc_linear_op(op) && op.a[1] >= gemm3_min_k) {  // 3xTF32 tcgen05 kernel fed straight from the rows and the staged weights
           vmg::Args a{};
           a.a_base = k.rows + (size_t)op.a[0] * C; a.a_pitch = C; a.a_rows = op.a[1];
           a.b_base = k.par + op.a[10]; a.b_pitch = op.a[11]; a.b_rows = op.a[12];
