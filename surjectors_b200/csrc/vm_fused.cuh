@@ -453,9 +453,12 @@ __device__ __forceinline__ void tm_fwd(const SplineTm& s, float v, bool forward,
 
 // VJP: cotangent of theta -> rows [th_row + c][sample] (p = &rows[th_row * C + sample]); returns the cotangent of v.
 // After tm_locate<KEEP> the accumulator holds exp(theta - max) for widths / heights: the sweep is a multiply per entry.
-template <int NCH, bool FULL>
+// release(): called as soon as the last tensor-memory read of this dim has completed -- the accumulator goes back to the
+// MMA issuer while the second side's cotangents and the slope rows are still being computed and stored (the VJP holds an
+// accumulator for its whole epilogue otherwise: per pair of dims the issuer idled for the length of one epilogue).
+template <int NCH, bool FULL, class Release>
 __device__ __forceinline__ float tm_bwd(const SplineTm& s, float* __restrict__ p, size_t C, float v, bool forward, float g_out, float g_ld,
-                                        long long* tt) {
+                                        long long* tt, Release&& release) {
   const long long c0 = tt ? clock64() : 0;
   vm::RqsBin b;
   tm_locate<NCH, FULL, true>(s, v, forward, b);
@@ -471,27 +474,35 @@ __device__ __forceinline__ float tm_bwd(const SplineTm& s, float* __restrict__ p
   for (int side = 0; side < 2; ++side) {
     const float cz = tail ? 0.0f : span / (side ? b.zh : b.zw);
     const float A = side ? G.Ah : G.Aw, Bc = side ? G.Bh : G.Bw, dot = side ? G.doth : G.dotw;
+    const float cA = cz * (A - dot), cB = cz * (Bc - dot), c0 = -cz * dot;  // coefficient of exp(theta_k - max) below / at / above the bin
     Chunk e[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) tm_issue(s.taddr + (uint32_t)(side * K + 16 * c), e[c]);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) tm_wait(e[c]);
+    if (side == 1) release();
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int k = 16 * c + i;
         if (FULL || k < K) {
-          const float sc = k < kb ? A : (k == kb ? Bc : 0.0f);
-          p[(size_t)(side * K + k) * C] = cz * CF(e[c], i) * (sc - dot);
+          p[(size_t)(side * K + k) * C] = CF(e[c], i) * (k < kb ? cA : (k == kb ? cB : c0));
         }
       }
   }
-  for (int k = 0; k <= K; ++k) {
-    float g = 0.0f;
-    if (tail) { if (2 * K + k == G.ks) g = G.g_tail; }
-    else { if (k == kb) g = G.g_u0; if (k == kb + 1) g = G.g_u1; }
-    p[(size_t)(2 * K + k) * C] = g;
+  // the K + 1 slope parameters: all but two (one in a tail) have zero cotangent -- zero the rows, then patch (same thread,
+  // same addresses: program order)
+  {
+    float* q = p + (size_t)(2 * K) * C;
+#pragma unroll 8
+    for (int k = 0; k <= K; ++k) q[(size_t)k * C] = 0.0f;
+    if (tail) {
+      if (G.ks >= 2 * K && G.ks <= 3 * K) p[(size_t)G.ks * C] = G.g_tail;
+    } else {
+      q[(size_t)kb * C] = G.g_u0;
+      q[(size_t)(kb + 1) * C] = G.g_u1;
+    }
   }
   if (tt) { tt[0] += c1 - c0; tt[1] += c2 - c1; tt[2] += clock64() - c2; }
   return G.g_v;
@@ -773,14 +784,20 @@ vg_fused_rqs(const __grid_constant__ Desc d, float* __restrict__ rows, int C, in
           float* gp = rows + (size_t)(d.th_row + j * d.P) * C + col;
           float g_v = 0.0f;
           with_chunks(d.K_bins, [&](auto nch, auto full) {
-            g_v = tm_bwd<decltype(nch)::value, decltype(full)::value>(th, gp, (size_t)C, v, forward_spline, g_out, g_lp, rec ? tt : nullptr);
+            g_v = tm_bwd<decltype(nch)::value, decltype(full)::value>(th, gp, (size_t)C, v, forward_spline, g_out, g_lp, rec ? tt : nullptr, [&] {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(d_empty + buf);
+            });
           });
           rows[(size_t)(d.gin_row + dim) * C + col] = g_v;
         }
         if (rec) { w3 += clock64() - t_d; w4 += t_d - t_c; }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(d_empty + buf);
+        if (MODE == 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d_empty + buf);
+        }
       }
       // ---- log-det of the tile: both groups' halves -> the lp row
       if (MODE == 0) {
