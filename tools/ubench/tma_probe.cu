@@ -3,8 +3,11 @@
 //   1. K-major operands (rows [r][k], k contiguous): box {16 k, rows} with CU_TENSOR_MAP_SWIZZLE_64B -> UMMA descriptor
 //      layout SWIZZLE_64B, SBO = 512 B (8 rows x 64 B), k step of 8 = +32 B on the start address
 //   2. an MN-major A operand (rows [k][m], m contiguous -- the activations of LINEAR as they live in the workspace):
-//      four boxes {32 m, 16 k} with CU_TENSOR_MAP_SWIZZLE_128B -> descriptor layout SWIZZLE_128B, LBO = 2048 B (next 32 m),
-//      SBO = 1024 B (next 8 k), instruction-descriptor bit 15 (A is MN-major), k step of 8 = +1024 B
+//      four boxes {32 m, 16 k} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks swizzled within 128 bytes: chunk
+//      (m % 32) / 8 of k row r lands at chunk position ((m % 32) / 8) ^ (r % 4)) -> descriptor layout code 1
+//      (SWIZZLE_128B_BASE32B), LBO = 2048 B (next 32 m), SBO = 512 B (next 4 k), instruction-descriptor bit 15 (A is
+//      MN-major), k step of 8 = +1024 B.  The plain 128-byte swizzle (layout code 2) does NOT work for a 32-bit MN-major
+//      operand: those variants are run too and must mismatch (they document what was tried).
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I surjectors_b200/csrc -I include tools/ubench/tma_probe.cu -o tools/ubench/tma_probe
 #include <cuda.h>
 
@@ -120,12 +123,11 @@ int main() {
   float* dD;
   CK(cudaMalloc(&dD, 8192));
   struct Var { int mode; uint32_t lbo, sbo, layout, idesc, kadv; const char* name; int atom32; };
-  const Var vars[] = {{0, 0, 0, 0, 0, 0, "K-major SW64", 0},
-                      {1, 2048, 1024, 1, 1u << 15, 1024, "MN SW128_ATOM_32B, layout 1, lbo 2048 sbo 1024", 1},
-                      {1, 1024, 2048, 1, 1u << 15, 1024, "MN SW128_ATOM_32B, layout 1, lbo 1024 sbo 2048", 1},
-                      {1, 2048, 512, 1, 1u << 15, 1024, "MN SW128_ATOM_32B, layout 1, lbo 2048 sbo 512", 1},
-                      {1, 2048, 1024, 2, 1u << 15, 1024, "MN SW128_ATOM_32B image, layout 2", 1},
-                      {1, 2048, 1024, 1, 1u << 15, 1024, "MN SW128 image, layout 1", 0}};
+  const Var vars[] = {{0, 0, 0, 0, 0, 0, "K-major, 64B swizzle (layout 4, SBO 512)", 0},
+                      {1, 2048, 512, 1, 1u << 15, 1024, "MN-major, 128B swizzle on 32B atoms (layout 1, LBO 2048, SBO 512)", 1},
+                      {1, 2048, 1024, 1, 1u << 15, 1024, "[expected to mismatch] same, SBO 1024", 1},
+                      {1, 2048, 1024, 2, 1u << 15, 1024, "[expected to mismatch] plain 128B swizzle image, layout 2", 0},
+                      {1, 2048, 1024, 1, 1u << 15, 1024, "[expected to mismatch] plain 128B swizzle image, layout 1", 0}};
   for (const Var& v : vars) {
     const int mode = v.mode;
     CUtensorMap ma = mode == 0 ? make_map(enc, dA, K, M, K, 16, 128, CU_TENSOR_MAP_SWIZZLE_64B) : make_map(enc, dAt, M, K, M, 32, 16, v.atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
