@@ -123,7 +123,8 @@ __global__ void vg_scalars(const ScalarJob* __restrict__ jobs, int n_jobs, const
 }
 
 // a run of per-sample ops over one chunk; lp / g_lp live in rows ROW_LP / ROW_GLP between launches
-__global__ void __launch_bounds__(128)
+template <bool LITE>
+__global__ void __launch_bounds__(128, LITE ? 8 : 1)
 vg_elem(const Op* __restrict__ ops, int n_ops, int first, Io io, float* __restrict__ rows, int C, long long base,
         long long B, const int32_t* __restrict__ itab, const float* __restrict__ scal, float* __restrict__ scal_g,
         float* __restrict__ loss_acc) {
@@ -144,7 +145,7 @@ vg_elem(const Op* __restrict__ ops, int n_ops, int first, Io io, float* __restri
   bool stored = false;
   for (int pc = 0; pc < n_ops; ++pc) {
     const Op op = ops[pc];
-    exec_simple<128, 1, true>(c, op, io, lp_total);
+    exec_simple<128, 1, true, LITE>(c, op, io, lp_total);
     stored |= op.code == OP_STORE_LP;
   }
   c.row(ROW_LP)[0] = c.lp[0];
@@ -153,6 +154,31 @@ vg_elem(const Op* __restrict__ ops, int n_ops, int first, Io io, float* __restri
     for (int o = 16; o > 0; o >>= 1) lp_total += __shfl_xor_sync(0xffffffffu, lp_total, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(loss_acc, lp_total);
   }
+}
+
+// ---- a per-sample run that is ONE activation derivative (between an input-gradient product and the weight-gradient
+// contraction of the layer below: emit_mlp_bwd) as a streaming kernel: g[k][s] = act'(pre[k][s]) g[k][s], four samples per
+// thread as a float4, AB_ROWS rows per CTA, two rows in flight.  vg_elem carries every op of the interpreter (120
+// registers, 16 warps per SM): it reaches the HBM rate on relu but runs swish's derivative at 0.25 ms per 256 rows x
+// 262 144 samples against 0.11 ms of memory time.
+constexpr int AB_ROWS = 8;
+__global__ void __launch_bounds__(256)
+vg_act_bwd_rows(float* __restrict__ rows, long long C, int g_row, int pre_row, int n, int act, int cols) {
+  const int c4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c4 >= cols) return;
+  const int k0 = blockIdx.y * AB_ROWS, k1 = min(n, k0 + AB_ROWS);
+  with_act(act, [&](auto tag) {
+    constexpr int ACT = decltype(tag)::value;
+    for (int k = k0; k < k1; k += 2) {
+      const bool two = k + 1 < k1;
+      float4* gp0 = reinterpret_cast<float4*>(rows + (long long)(g_row + k) * C + c4);
+      float4* gp1 = reinterpret_cast<float4*>(rows + (long long)(g_row + k + (two ? 1 : 0)) * C + c4);
+      const float4 g0 = *gp0, a0 = *reinterpret_cast<const float4*>(rows + (long long)(pre_row + k) * C + c4);
+      const float4 g1 = *gp1, a1 = *reinterpret_cast<const float4*>(rows + (long long)(pre_row + k + (two ? 1 : 0)) * C + c4);
+      *gp0 = make_float4(act_bwd_fast(ACT, a0.x, g0.x), act_bwd_fast(ACT, a0.y, g0.y), act_bwd_fast(ACT, a0.z, g0.z), act_bwd_fast(ACT, a0.w, g0.w));
+      if (two) *gp1 = make_float4(act_bwd_fast(ACT, a1.x, g1.x), act_bwd_fast(ACT, a1.y, g1.y), act_bwd_fast(ACT, a1.z, g1.z), act_bwd_fast(ACT, a1.w, g1.w));
+    }
+  });
 }
 
 // ---- out[j][s] = act(b[j] (+ prev) + sum_i W[i*ld + j] in[i][s]);  CTA tile 128 samples x 64 outputs
@@ -753,7 +779,7 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
         std::memcpy(&d, g.desc.data(), sizeof d);
         if (g.gather >= 0) {
           prof::Scope ps(st, prof::ELEM, 0.0);
-          vm::vg_elem<<<cols / 128, 128, 0, st>>>(d_ops + g.gather, 1, 0, io, k.rows, C, base, B, P.itab, k.scal, k.scal_g, k.loss);
+          vm::vg_elem<true><<<cols / 128, 128, 0, st>>>(d_ops + g.gather, 1, 0, io, k.rows, C, base, B, P.itab, k.scal, k.scal_g, k.loss);
         }
         static const bool attr = [] {
           cudaFuncSetAttribute(vmaf::vg_maf_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -912,8 +938,15 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           fprintf(stderr, "\n");
         }
         prof::Scope ps(st, prof::ELEM, 0.0);
-        vm::vg_elem<<<cols / 128, 128, 0, st>>>(d_ops + pc, (int)(e - pc), first ? 1 : 0, io, k.rows, C, base, B, P.itab,
-                                              k.scal, k.scal_g, k.loss);
+        if (e == pc + 1 && !first && ops[pc].code == vm::OP_ACT_BWD) {  // a lone activation derivative: streaming kernel
+          dim3 grid((cols + 1023) / 1024, (ops[pc].a[2] + vm::AB_ROWS - 1) / vm::AB_ROWS);
+          vm::vg_act_bwd_rows<<<grid, 256, 0, st>>>(k.rows, (long long)C, ops[pc].a[0], ops[pc].a[1], ops[pc].a[2], ops[pc].a[3], cols);
+        } else {
+          bool lite = true;  // no spline op in the run: the copy of the interpreter without them (8 CTAs per SM instead of 4)
+          for (size_t q = pc; q < e; ++q) lite = lite && ops[q].code != vm::OP_RQS && ops[q].code != vm::OP_RQS_BWD;
+          if (lite) vm::vg_elem<true><<<cols / 128, 128, 0, st>>>(d_ops + pc, (int)(e - pc), first ? 1 : 0, io, k.rows, C, base, B, P.itab, k.scal, k.scal_g, k.loss);
+          else vm::vg_elem<false><<<cols / 128, 128, 0, st>>>(d_ops + pc, (int)(e - pc), first ? 1 : 0, io, k.rows, C, base, B, P.itab, k.scal, k.scal_g, k.loss);
+        }
         first = false;
         pc = e;
       }

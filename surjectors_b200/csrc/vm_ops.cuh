@@ -250,7 +250,10 @@ VM_DEV void op_normal_lp_bwd(Ctx<NT, S, FAR>& c, const Op& op) {
 
 // Executes one simple op; returns false if `op` is a matrix op the caller must handle.
 // lp_total accumulates the log-probs of valid samples stored by OP_STORE_LP (for the loss).
-template <int NT, int S, bool FAR>
+// LITE: without the spline ops (their register footprint sets the occupancy of the whole interpreter kernel; the per-op
+// executor launches runs that contain none of them -- all of them once the spline layers are fused -- on a copy built
+// without).
+template <int NT, int S, bool FAR, bool LITE = false>
 VM_DEV bool exec_simple(Ctx<NT, S, FAR>& c, const Op& op, const Io& io, float& lp_total) {
   constexpr int UR = FAR ? 8 : 1, UA = FAR ? 4 : 1;  // rows of loads in flight in the copy-like / activation loops
   switch (op.code) {
@@ -306,7 +309,7 @@ VM_DEV bool exec_simple(Ctx<NT, S, FAR>& c, const Op& op, const Io& io, float& l
         for (int s = 0; s < S; ++s) c.row(op.a[0] + k)[s * NT] = 0.0f;
       return true;
     case OP_AFFINE: op_affine<NT, S, FAR>(c, op); return true;
-    case OP_RQS: op_rqs<NT, S, FAR>(c, op); return true;
+    case OP_RQS: if constexpr (LITE) return false; else { op_rqs<NT, S, FAR>(c, op); return true; }
     case OP_NORMAL_LP: op_normal_lp<NT, S, FAR>(c, op); return true;
     case OP_NORMAL_SAMPLE:
       for (int j = 0; j < op.a[1]; ++j)
@@ -355,7 +358,7 @@ VM_DEV bool exec_simple(Ctx<NT, S, FAR>& c, const Op& op, const Io& io, float& l
       return true;
     case OP_NORMAL_LP_BWD: op_normal_lp_bwd<NT, S, FAR>(c, op); return true;
     case OP_AFFINE_BWD: op_affine_bwd<NT, S, FAR>(c, op); return true;
-    case OP_RQS_BWD: op_rqs_bwd<NT, S, FAR>(c, op); return true;
+    case OP_RQS_BWD: if constexpr (LITE) return false; else { op_rqs_bwd<NT, S, FAR>(c, op); return true; }
     case OP_ACT_BWD:
       for (int k0 = 0; k0 < op.a[2]; k0 += UA) {  // UA rows in flight
         float g[UA][S], a[UA][S];
