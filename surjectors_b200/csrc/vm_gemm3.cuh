@@ -237,13 +237,19 @@ __device__ __forceinline__ void drain_epilogue(const Args& g, int warp, int lane
         constexpr int ACT = decltype(tag)::value;
         for (int c0 = 0; c0 < n_write; c0 += 32) {
           uint32_t w[32];
-          if (n_stages > 0) { tm_ld32(t_acc + (uint32_t)c0, w); tm_ld_wait(); }
+          float prev[32];
+          if (n_stages > 0) tm_ld32(t_acc + (uint32_t)c0, w);
+          if (g.accumulate) {  // requested together, before this batch's stores (see vg_linear_pipe)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) prev[i] = c0 + i < n_write ? g.rows[(long long)(acc_row + n0 + c0 + i) * g.C + col] : 0.0f;
+          }
+          if (n_stages > 0) tm_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int j = n0 + c0 + i;
             if (c0 + i < n_write) {
               float x = (n_stages > 0 ? __uint_as_float(w[i]) : 0.0f) + (g.b_off >= 0 ? __ldg(g.par + g.b_off + j) : 0.0f);
-              if (g.accumulate) x += g.rows[(long long)(acc_row + j) * g.C + col];
+              if (g.accumulate) x += prev[i];
               if (g.pre_row >= 0) g.rows[(long long)(g.pre_row + j) * g.C + col] = x;
               g.rows[(long long)(g.out_row + j) * g.C + col] = vm::act_fwd(ACT, x);
             }

@@ -352,7 +352,10 @@ inline int chunk_cols(int64_t B, int n_rows) {
   c = std::max<int64_t>(128, std::min(c, cap));
   return (int)c;
 }
-inline bool tc_linear_op(const vm::Op& op) { return op.code == vm::OP_LINEAR && op.a[1] >= 32 && op.a[5] >= 32; }
+inline bool tc_linear_op(const vm::Op& op) {
+  static const int min_k = [] { const char* e = getenv("SURJ_B200_TC_MINK"); return e ? atoi(e) : 32; }();
+  return op.code == vm::OP_LINEAR && op.a[1] >= min_k && op.a[5] >= 32;
+}
 
 // tensor-core bookkeeping of one program: tiled-weight offsets (deduplicated by matrix) and scratch sizes
 const VmTcInfo& tc_info(const VmPlan* v, int prog) {

@@ -577,14 +577,26 @@ vg_linear_pipe(vm::Op op, float* __restrict__ rows, int C, const float* __restri
     const int acc_row = pre_row >= 0 ? pre_row : out_row;
     vm::with_act(act, [&](auto tag) {
       constexpr int ACT = decltype(tag)::value;
+      // the rows an accumulating product adds to are requested 32 at a time, BEFORE that batch's stores: a load placed after
+      // a store to the same array cannot be hoisted by the compiler, and one dependent global load per output (128 per
+      // thread, ~700 cycles each) cost an accumulating LINEAR four times its mainloop (cfg5: the masked first layer adds
+      // onto the context Linear)
 #pragma unroll
-      for (int c = 0; c < TN; ++c) {
-        const int j = j0 + c;
-        if (c < n_valid) {
-          float x = acc[c] + (b_off >= 0 ? __ldg(par + b_off + j) : 0.0f);
-          if (accumulate) x += rows[(size_t)(acc_row + j) * C + col];
-          if (pre_row >= 0) rows[(size_t)(pre_row + j) * C + col] = x;
-          rows[(size_t)(out_row + j) * C + col] = vm::act_fwd(ACT, x);
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        float prev[32];
+        if (accumulate) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) prev[q] = c0 + q < n_valid ? rows[(size_t)(acc_row + j0 + c0 + q) * C + col] : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int c = c0 + q, j = j0 + c;
+          if (c < n_valid) {
+            float x = acc[c] + (b_off >= 0 ? __ldg(par + b_off + j) : 0.0f);
+            if (accumulate) x += prev[q];
+            if (pre_row >= 0) rows[(size_t)(pre_row + j) * C + col] = x;
+            rows[(size_t)(out_row + j) * C + col] = vm::act_fwd(ACT, x);
+          }
         }
       }
     });
