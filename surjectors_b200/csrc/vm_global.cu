@@ -258,6 +258,60 @@ vg_linear(Op op, float* __restrict__ rows, int C, const float* __restrict__ par)
   });
 }
 
+// ---- LINEAR with n_in <= 16 (the context Linear of a conditional MADE, made.py:80-84: 16 -> 512) as a streaming kernel:
+// a thread keeps the n_in inputs of two samples in registers and walks SK_J outputs, weights broadcast from shared
+// memory; every row is written as float2 per thread (256 contiguous bytes per warp).  (The 128 x 64 tile kernel above spends its time on set-up for one
+// 16-deep k step: 0.39 ms per 16 -> 512 layer at 262 144 samples against ~0.15 ms of memory time.)
+constexpr int SK_J = 64, SK_K = 16;
+__global__ void __launch_bounds__(256, 4)
+vg_linear_smallk(Op op, float* __restrict__ rows, int C, const float* __restrict__ par, int cols) {
+  const int in_row = op.a[0], n_in = op.a[1], w_off = op.a[2], ld = op.a[3], out_row = op.a[4], n_out = op.a[5],
+            b_off = op.a[6], act = op.a[7], accumulate = op.a[8], pre_row = op.a[9];
+  __shared__ float Ws[SK_K][SK_J];
+  __shared__ float Bs[SK_J];
+  const int tid = threadIdx.x, j0 = blockIdx.y * SK_J;
+  for (int idx = tid; idx < SK_K * SK_J; idx += 256) {
+    const int i = idx / SK_J, jj = idx % SK_J;
+    Ws[i][jj] = (i < n_in && j0 + jj < ld) ? par[w_off + (size_t)i * ld + j0 + jj] : 0.0f;
+  }
+  if (tid < SK_J) Bs[tid] = (b_off >= 0 && j0 + tid < n_out) ? par[b_off + j0 + tid] : 0.0f;
+  __syncthreads();
+  const int c2 = (blockIdx.x * 256 + tid) * 2;   // two samples per thread (32 input registers: four CTAs per SM)
+  if (c2 >= cols) return;
+  float2 x[SK_K];
+#pragma unroll
+  for (int i = 0; i < SK_K; ++i)
+    x[i] = i < n_in ? *reinterpret_cast<const float2*>(rows + (size_t)(in_row + i) * C + c2) : make_float2(0.f, 0.f);
+  const int acc_row = pre_row >= 0 ? pre_row : out_row;
+  const int j_end = min(SK_J, n_out - j0);
+  with_act(act, [&](auto tag) {
+    constexpr int ACT = decltype(tag)::value;
+    for (int jj0 = 0; jj0 < j_end; jj0 += 4) {
+      float2 prev[4];
+      if (accumulate) {  // requested together, before this batch's stores
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          prev[u] = jj0 + u < j_end ? *reinterpret_cast<const float2*>(rows + (size_t)(acc_row + j0 + jj0 + u) * C + c2) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (jj0 + u >= j_end) continue;
+        float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < SK_K; ++i) {
+          const float w = Ws[i][jj0 + u];
+          v.x = fmaf(w, x[i].x, v.x); v.y = fmaf(w, x[i].y, v.y);
+        }
+        v.x += Bs[jj0 + u]; v.y += Bs[jj0 + u];  // (products first, then the bias: the order of the tile kernel)
+        if (accumulate) { v.x += prev[u].x; v.y += prev[u].y; }
+        const size_t o = (size_t)(j0 + jj0 + u) * C + c2;
+        if (pre_row >= 0) *reinterpret_cast<float2*>(rows + (size_t)pre_row * C + o) = v;
+        *reinterpret_cast<float2*>(rows + (size_t)out_row * C + o) = make_float2(act_fwd(ACT, v.x), act_fwd(ACT, v.y));
+      }
+    }
+  });
+}
+
 // ---- grad[w_off + i*ld + j] += sum_s in[i][s] g[j][s]; grad[b_off + j] += sum_s g[j][s] (ones row).
 // CTA tile 64 x 64 outputs over a slab of samples; partial sums are added with atomics.
 constexpr int DBI = 64, DBJ = 64, DBK = 32, DLD = DBK + 4;
@@ -881,9 +935,15 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
           prof::Scope ps(st, prof::LINEAR_TC, fl);
           vmtc::vg_linear_tc<<<grid, vmtc::NTHR, vmtc::SMEM_BYTES, st>>>(op, k.rows, C, k.par);
         } else {
-          dim3 grid(cols / vm::LBM, (op.a[5] + vm::LBN - 1) / vm::LBN);
           prof::Scope ps(st, prof::LINEAR_SIMT, fl);
-          vm::vg_linear<<<grid, 256, 0, st>>>(op, k.rows, C, k.par);
+          static const bool smallk = [] { const char* e = getenv("SURJ_B200_SMALLK"); return !e || atoi(e) != 0; }();
+          if (smallk && op.a[1] <= vm::SK_K && op.a[5] >= 32) {  // short contraction, many outputs: streaming kernel
+            dim3 grid((cols + 511) / 512, (op.a[5] + vm::SK_J - 1) / vm::SK_J);
+            vm::vg_linear_smallk<<<grid, 256, 0, st>>>(op, k.rows, C, k.par, cols);
+          } else {
+            dim3 grid(cols / vm::LBM, (op.a[5] + vm::LBN - 1) / vm::LBN);
+            vm::vg_linear<<<grid, 256, 0, st>>>(op, k.rows, C, k.par);
+          }
         }
         ++pc;
       } else if (op.code == vm::OP_LINEAR_DW) {
