@@ -949,7 +949,8 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
       } else if (op.code == vm::OP_LINEAR_DW) {
         const int NA = op.a[1] + (op.a[6] >= 0 ? 1 : 0), NG = op.a[3];
         const double fl = 2.0 * tci.nnz[pc] * (double)cols;
-        if (gemm3 && NA >= 32 && NG >= 32) {
+        static const int dw_min_a = [] { const char* e = getenv("SURJ_B200_DW_MINA"); return e ? atoi(e) : 8; }();  // (cfg5, 16-input context weights: 0.45 ms per SIMT launch against 0.14 ms here)
+        if (gemm3 && NA >= dw_min_a && NG >= 32) {
           vmg::Args a{};
           a.a_base = k.rows + (size_t)op.a[0] * C; a.a_pitch = C; a.a_rows = op.a[1];
           a.b_base = k.rows + (size_t)op.a[2] * C; a.b_pitch = C; a.b_rows = NG;
