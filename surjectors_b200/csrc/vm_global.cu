@@ -888,9 +888,10 @@ int vm_global_run(VmPlan* v, cudaStream_t st, int prog, int with_base, const flo
       }
       if (op.code == vm::OP_LINEAR) {
         const double fl = 2.0 * tci.nnz[pc] * (double)cols;
-        // (long contractions only -- the input gradient through a spline layer's 1544 .. 6176 thetas; on K <= 512 its
-        // one-tile-per-CTA set-up costs more than it saves: cfg5's MADE layers measured 777 vs 520 ms per train step)
-        static const int gemm3_min_k = [] { const char* e = getenv("SURJ_B200_GEMM3_MINK"); return e ? atoi(e) : 1024; }();
+        // (long contractions only -- the input gradient through a spline layer's 1544 .. 6176 thetas, cfg5's 512-wide MADE
+        // layers; below that its one-tile-per-CTA set-up costs more than the re-tiling pass it saves: cfg5 train step
+        // 766 / 749 / 772 ms with the threshold at 1024 / 512 / 128)
+        static const int gemm3_min_k = [] { const char* e = getenv("SURJ_B200_GEMM3_MINK"); return e ? atoi(e) : 512; }();
         if (gemm3 && pc > grad_from && tc_linear_op(op) && op.a[1] >= gemm3_min_k) {  // 3xTF32 tcgen05 kernel fed straight from the rows and the staged weights
           vmg::Args a{};
           a.a_base = k.rows + (size_t)op.a[0] * C; a.a_pitch = C; a.a_rows = op.a[1];
